@@ -1,0 +1,217 @@
+// common.cuh -- shared host/device plumbing of libsepcore (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <vector>
+
+#include "../../include/sepcore.h"
+
+namespace sep {
+
+// ------------------------------------------------------------------ errors
+void set_error(const char *fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+#define SEP_CUDA(expr)                                                              \
+  do {                                                                              \
+    cudaError_t e__ = (expr);                                                       \
+    if (e__ != cudaSuccess) {                                                       \
+      ::sep::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,         \
+                       cudaGetErrorString(e__));                                    \
+      return SEP_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+#define SEP_REQUIRE(cond, ...)                                                      \
+  do {                                                                              \
+    if (!(cond)) {                                                                  \
+      ::sep::set_error(__VA_ARGS__);                                                \
+      return SEP_ERR_INVALID;                                                       \
+    }                                                                               \
+  } while (0)
+
+// counts one kernel launch and checks the launch error
+#define SEP_LAUNCHED()                                                              \
+  do {                                                                              \
+    ::sep::g_launches.fetch_add(1, std::memory_order_relaxed);                      \
+    SEP_CUDA(cudaGetLastError());                                                   \
+  } while (0)
+
+}  // namespace sep
+
+// ------------------------------------------------------------------ plan
+struct sep_plan {
+  int size = 0;     // n_fft
+  int shift = 0;    // hop
+  int bins = 0;     // size/2 + 1
+  int half = 0;     // size/2 (length of the complex FFT behind a real one)
+  int hops = 0;     // size/shift when divisible, else 0 (no iSTFT / fused path)
+  int fading = 1;
+  int pad = 0;      // size - shift when fading
+  int device = 0;
+  int sm_count = 148;
+  int max_smem = 0;  // opt-in dynamic shared memory per block
+  std::vector<double> window;  // analysis, float64 (host)
+  std::vector<double> synth;   // biorthogonal synthesis window (cell 38), float64
+  // device tables (float32)
+  float *d_win_half = nullptr;   // 0.5 * analysis window   (half-size real FFT)
+  float *d_win_full = nullptr;   // analysis window          (pair-packed FFT)
+  float *d_syn = nullptr;        // size * synth / size = w/q, times 1/size (irfft norm)
+  float2 *d_tw_half = nullptr;   // exp(-2 pi i k / half), k < half
+  float2 *d_tw_full = nullptr;   // exp(-2 pi i k / size), k <= half
+  float2 *d_tw16 = nullptr;      // exp(-2 pi i p*k / 256) [16][16] for the 16x16 FFT
+};
+
+namespace sep {
+
+// Stream-ordered scratch: every entry point allocates what it needs on its own
+// stream, so calls are re-entrant.  The pool keeps freed blocks (threshold
+// raised at plan creation), so steady-state calls do not hit the driver.
+struct Scratch {
+  cudaStream_t stream;
+  std::vector<void *> blocks;
+  explicit Scratch(cudaStream_t s) : stream(s) {}
+  ~Scratch() {
+    for (void *p : blocks) cudaFreeAsync(p, stream);
+  }
+  template <typename T>
+  int alloc(T **out, size_t count) {
+    void *p = nullptr;
+    size_t bytes = count * sizeof(T);
+    if (bytes == 0) bytes = sizeof(T);
+    cudaError_t e = cudaMallocAsync(&p, bytes, stream);
+    if (e != cudaSuccess) {
+      set_error("cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+      return SEP_ERR_NOMEM;
+    }
+    blocks.push_back(p);
+    *out = static_cast<T *>(p);
+    return SEP_OK;
+  }
+};
+
+// Stages a caller buffer onto the device when it lives in host memory.
+template <typename T>
+inline int stage_in(Scratch &s, const T *src, size_t count, int mem, const T **dev) {
+  if (src == nullptr) {
+    *dev = nullptr;
+    return SEP_OK;
+  }
+  if (mem == SEP_MEM_DEVICE) {
+    *dev = src;
+    return SEP_OK;
+  }
+  T *d = nullptr;
+  int rc = s.alloc(&d, count);
+  if (rc != SEP_OK) return rc;
+  SEP_CUDA(cudaMemcpyAsync(d, src, count * sizeof(T), cudaMemcpyHostToDevice, s.stream));
+  *dev = d;
+  return SEP_OK;
+}
+
+template <typename T>
+inline int stage_out(Scratch &s, T *dst, size_t count, int mem, T **dev) {
+  if (dst == nullptr) {
+    *dev = nullptr;
+    return SEP_OK;
+  }
+  if (mem == SEP_MEM_DEVICE) {
+    *dev = dst;
+    return SEP_OK;
+  }
+  return s.alloc(dev, count);
+}
+
+template <typename T>
+inline int copy_back(Scratch &s, T *dst, const T *dev, size_t count, int mem) {
+  if (dst == nullptr || mem == SEP_MEM_DEVICE) return SEP_OK;
+  SEP_CUDA(cudaMemcpyAsync(dst, dev, count * sizeof(T), cudaMemcpyDeviceToHost, s.stream));
+  return SEP_OK;
+}
+
+inline int finish(Scratch &s, int mem) {
+  if (mem == SEP_MEM_HOST) SEP_CUDA(cudaStreamSynchronize(s.stream));
+  return SEP_OK;
+}
+
+inline int check_mem(int mem) {
+  if (mem != SEP_MEM_HOST && mem != SEP_MEM_DEVICE) {
+    set_error("mem must be SEP_MEM_HOST or SEP_MEM_DEVICE, got %d", mem);
+    return SEP_ERR_INVALID;
+  }
+  return SEP_OK;
+}
+
+inline int factorial(int n) {
+  int f = 1;
+  for (int i = 2; i <= n; ++i) f *= i;
+  return f;
+}
+
+// ------------------------------------------------------------------ device helpers
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {  // a * conj(b)
+  return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Deterministic block reduction of NV doubles per thread: warp butterflies, then
+// warp 0 adds the per-warp partials in warp order.  `red` is shared scratch of
+// at least NV * (blockDim.x / 32) doubles.  Result valid in thread 0.
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double *red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red[warp * NV + i] = v[i];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double s = 0.0;
+      for (int w = 0; w < nwarp; ++w) s += red[w * NV + i];
+      v[i] = s;
+    }
+  }
+}
+
+// Lexicographic permutation p of n (n <= 4) into out[0..n).
+__device__ __forceinline__ void nth_permutation(int n, int p, int *out) {
+  int pool[SEP_MAX_SOURCES];
+  for (int i = 0; i < n; ++i) pool[i] = i;
+  int f = 1;
+  for (int i = 2; i < n; ++i) f *= i;  // (n-1)!
+  int left = n;
+  for (int i = 0; i < n; ++i) {
+    int q = p / f;
+    p -= q * f;
+    out[i] = pool[q];
+    for (int k = q; k + 1 < left; ++k) pool[k] = pool[k + 1];
+    --left;
+    if (left > 1) f /= left;
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace sep

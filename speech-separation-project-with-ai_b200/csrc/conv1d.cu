@@ -1,0 +1,128 @@
+// conv1d.cu -- Keras Conv1D forward ("learned filterbank" front end), fp32 SIMT.
+//
+// Reference: Conv1D(filters=129, kernel_size=2, activation='sigmoid',
+// padding='same') on [B, K, 40] segments, Raw_with_Convlayer.ipynb:389 (cell
+// 13); segmentation :83-100 (cell 2).
+//
+// out[b, r, n] = act(bias[n] + sum_{j, c} x[b, r*stride + j - left, c] * W[j, c, n]).
+// Because the rows of x are contiguous, the im2col row of output r is the
+// contiguous span xflat[(r*stride - left) * c_in ... + taps*c_in): the
+// contraction is a [rows_out, taps*c_in] x [taps*c_in, filters] GEMM whose A
+// operand is an overlapping strided view -- no im2col buffer is materialised.
+// 64 x 64 output tile per CTA, 4 x 4 register micro-tile per thread, K staged
+// through shared memory 16 at a time.  (The tcgen05 variant for the BASELINE
+// N=256/L=16 shape is tracked in DESIGN.md.)
+#include "common.cuh"
+
+namespace sep {
+
+constexpr int kTM = 64, kTN = 64, kTK = 16;
+
+__device__ __forceinline__ float activate(float v, int act) {
+  if (act == SEP_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+  if (act == SEP_ACT_RELU) return fmaxf(v, 0.f);
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+conv1d_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
+              int rows, int c_in, int taps, int filters, int stride, int left, int rows_out,
+              int act, float *__restrict__ out) {
+  __shared__ float As[kTK][kTM + 4];
+  __shared__ float Bs[kTK][kTN + 4];
+  const int b = blockIdx.z, r0 = blockIdx.x * kTM, n0 = blockIdx.y * kTN;
+  const int K = taps * c_in;
+  const float *xb = x + static_cast<int64_t>(b) * rows * c_in;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16 threads, 4 x 4 outputs each
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += kTK) {
+    // A tile: As[kk][r] = x[b, (r0+r)*stride - left + j, c], (j, c) = divmod(k0+kk, c_in)
+    for (int e = threadIdx.x; e < kTK * kTM; e += 256) {
+      const int kk = e % kTK, r = e / kTK;
+      const int k = k0 + kk, ro = r0 + r;
+      float v = 0.f;
+      if (k < K && ro < rows_out) {
+        const int j = k / c_in, c = k - j * c_in;
+        const int row = ro * stride - left + j;
+        if (row >= 0 && row < rows) v = __ldg(xb + static_cast<int64_t>(row) * c_in + c);
+      }
+      As[kk][r] = v;
+    }
+    for (int e = threadIdx.x; e < kTK * kTN; e += 256) {
+      const int n = e % kTN, kk = e / kTN;
+      const int k = k0 + kk;
+      Bs[kk][n] = (k < K && n0 + n < filters) ? __ldg(w + static_cast<int64_t>(k) * filters + n0 + n) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kTK; ++kk) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bb[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ro = r0 + ty * 4 + i;
+    if (ro >= rows_out) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= filters) continue;
+      const float v = acc[i][j] + (bias ? __ldg(bias + n) : 0.f);
+      out[(static_cast<int64_t>(b) * rows_out + ro) * filters + n] = activate(v, act);
+    }
+  }
+}
+
+}  // namespace sep
+
+using namespace sep;
+
+extern "C" int sep_conv1d_f32(const float *x, const float *kernel, const float *bias, int batch,
+                              int rows, int c_in, int taps, int filters, int stride, int padding,
+                              int activation, float *out, int mem, void *stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SEP_REQUIRE(x && kernel && out, "sep_conv1d_f32: null argument");
+  SEP_REQUIRE(batch >= 1 && rows >= 1 && c_in >= 1 && taps >= 1 && filters >= 1 && stride >= 1,
+              "sep_conv1d_f32: bad shape");
+  SEP_REQUIRE(padding == SEP_PAD_VALID || padding == SEP_PAD_SAME, "sep_conv1d_f32: bad padding code %d", padding);
+  SEP_REQUIRE(activation >= SEP_ACT_LINEAR && activation <= SEP_ACT_RELU, "sep_conv1d_f32: bad activation code %d", activation);
+  int rc = check_mem(mem);
+  if (rc) return rc;
+  int rows_out, left = 0;
+  if (padding == SEP_PAD_SAME) {   // TensorFlow 'same': left = total / 2, surplus on the right
+    rows_out = (rows + stride - 1) / stride;
+    const int total = std::max((rows_out - 1) * stride + taps - rows, 0);
+    left = total / 2;
+  } else {
+    SEP_REQUIRE(rows >= taps, "sep_conv1d_f32: 'valid' padding needs rows >= taps");
+    rows_out = (rows - taps) / stride + 1;
+  }
+  Scratch s(stream);
+  const float *d_x, *d_w, *d_b;
+  float *d_out;
+  if ((rc = stage_in(s, x, static_cast<size_t>(batch) * rows * c_in, mem, &d_x))) return rc;
+  if ((rc = stage_in(s, kernel, static_cast<size_t>(taps) * c_in * filters, mem, &d_w))) return rc;
+  if ((rc = stage_in(s, bias, static_cast<size_t>(filters), mem, &d_b))) return rc;
+  const size_t n_out = static_cast<size_t>(batch) * rows_out * filters;
+  if ((rc = stage_out(s, out, n_out, mem, &d_out))) return rc;
+  dim3 grid((rows_out + kTM - 1) / kTM, (filters + kTN - 1) / kTN, batch);
+  conv1d_kernel<<<grid, 256, 0, stream>>>(d_x, d_w, d_b, rows, c_in, taps, filters, stride, left,
+                                          rows_out, activation, d_out);
+  SEP_LAUNCHED();
+  if ((rc = copy_back(s, out, d_out, n_out, mem))) return rc;
+  return finish(s, mem);
+}

@@ -1,0 +1,55 @@
+"""Conv1D "learned filterbank" front end of Raw_with_Convlayer on the GPU.
+
+Reference: segmentation Raw_with_Convlayer.ipynb:83-100 (cell 2); layer
+Conv1D(filters=129, kernel_size=2, activation='sigmoid', padding='same') :389
+(cell 13); mask multiply :402-403.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+from ._buffers import as_f32_host, current_stream, is_device_tensor, mem_kind, ptr, require_f32_cuda
+
+
+def segment_raw(wave, seg_len=40):
+    """K = ceil(N / L) non-overlapping rows, zero padded (cell 2 :83-96). Host reshape, no compute."""
+    wave = np.asarray(wave)
+    k = int(np.ceil(len(wave) / seg_len))
+    padded = np.concatenate([wave, np.zeros(k * seg_len - len(wave), dtype=wave.dtype)])
+    return np.reshape(padded, [k, seg_len])
+
+
+def conv1d(x, kernel, bias=None, stride=1, padding="same", activation=None):
+    """Keras Conv1D forward: x [B, K, C_in], kernel [taps, C_in, N] (Keras layout),
+    bias [N] -> [B, K_out, N] float32 with the activation fused."""
+    lib = _lib.load()
+    dev = is_device_tensor(x)
+    if dev:
+        import torch
+
+        xx = require_f32_cuda(x, "x")
+        ww = require_f32_cuda(kernel, "kernel")
+        bb = None if bias is None else require_f32_cuda(bias, "bias")
+    else:
+        xx, ww = as_f32_host(x), as_f32_host(kernel)
+        bb = None if bias is None else as_f32_host(bias)
+    if xx.ndim != 3 or ww.ndim != 3 or int(ww.shape[1]) != int(xx.shape[2]):
+        raise ValueError("x must be [B, K, C_in] and kernel [taps, C_in, N]")
+    batch, rows, c_in = (int(v) for v in xx.shape)
+    taps, _, filters = (int(v) for v in ww.shape)
+    if padding == "same":
+        rows_out = -(-rows // stride)
+    elif padding == "valid":
+        rows_out = (rows - taps) // stride + 1
+    else:
+        raise ValueError("padding must be 'same' or 'valid'")
+    mem = mem_kind(xx, ww, bb)
+    if dev:
+        out = torch.empty((batch, rows_out, filters), dtype=torch.float32, device=xx.device)
+    else:
+        out = np.empty((batch, rows_out, filters), dtype=np.float32)
+    _lib.check(lib.sep_conv1d_f32(ptr(xx), ptr(ww), ptr(bb), batch, rows, c_in, taps, filters,
+                                  int(stride), _lib.PAD[padding], _lib.ACT[activation], ptr(out), mem,
+                                  current_stream(mem, xx if dev else None)), "sep_conv1d_f32")
+    return out

@@ -1,0 +1,407 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the Python host
+mirror of the reference's signatures) against the CPU oracle on the same seeded
+inputs and against the committed golden vectors.
+
+Tolerances (BASELINE.json north_star): selected permutation bit-exact; spectra
+and waveforms within 1e-4 relative (fp32 vs the fp64 oracle; relative to the
+array scale); SI-SDR / SDR within 0.01 dB; PIT loss 1e-5 relative.
+"""
+import numpy as np
+import pytest
+import scipy.signal.windows as windows
+
+from conftest import rel_err, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL_REL = 1e-4      # spectra / waveforms, fp32 vs fp64 oracle
+TOL_L2 = 2e-6       # typical fp32 FFT round-off, much tighter than the contract
+TOL_DB = 0.01       # SI-SDR / SDR
+TOL_LOSS = 1e-5     # PIT loss, relative
+
+CONFIGS = {
+    "blackman_256_128": dict(size=256, shift=128, window=windows.blackman),   # reference default
+    "blackman_256_64": dict(size=256, shift=64, window=windows.blackman),
+    "hann_256_64": dict(size=256, shift=64, window=windows.hann),            # BASELINE cfg1/2
+    "hann_512_128": dict(size=512, shift=128, window=windows.hann),          # BASELINE cfg4
+    "hamming_128_32": dict(size=128, shift=32, window=windows.hamming),
+    "blackman_1024_256": dict(size=1024, shift=256, window=windows.blackman),  # signature default
+}
+
+
+@pytest.fixture(scope="module")
+def sep():
+    import sepcore
+    return sepcore
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import signal_path
+    return signal_path
+
+
+# ----------------------------------------------------------------- a3 stft
+@pytest.mark.parametrize("key", list(CONFIGS))
+def test_stft_matches_reference_run(sep, reference_run, key):
+    got = sep.stft(reference_run["wave"], time_dim=0, **CONFIGS[key])
+    want = reference_run[f"stft_{key}"]
+    assert got.shape == want.shape and got.dtype == np.complex128
+    assert rel_err(got, want) < TOL_REL
+    assert rel_l2(got, want) < TOL_L2
+
+
+def test_stft_variants(sep, reference_run):
+    w = reference_run["wave"]
+    got = sep.stft(w, time_dim=0, size=256, shift=128, fading=False)
+    assert got.shape == reference_run["stft_nofade"].shape
+    assert rel_err(got, reference_run["stft_nofade"]) < TOL_REL
+    got = sep.stft(w, time_dim=0, size=256, shift=128, window_length=200)
+    assert rel_err(got, reference_run["stft_winlen200"]) < TOL_REL
+    b = reference_run["wave_batch"]
+    got = sep.stft(b, size=256, shift=128)                 # time_dim=None -> largest dim
+    assert got.shape == reference_run["stft_batch_default_dim"].shape
+    assert rel_err(got, reference_run["stft_batch_default_dim"]) < TOL_REL
+    got = sep.stft(np.ascontiguousarray(b.T), time_dim=0, size=256, shift=128)
+    assert got.shape == reference_run["stft_batch_time0"].shape
+    assert rel_err(got, reference_run["stft_batch_time0"]) < TOL_REL
+
+
+def test_stft_edge_lengths(sep, oracle):
+    rng = np.random.default_rng(5)
+    for n in (1, 100, 255, 256, 257, 383, 384, 385, 1000):
+        x = rng.standard_normal(n).astype(np.float32)
+        got = sep.stft(x, time_dim=0, size=256, shift=128)
+        want = oracle.stft(x, time_dim=0, size=256, shift=128)
+        assert got.shape == want.shape, n
+        assert rel_err(got, want) < TOL_REL, n
+    # shift that does not divide size is legal for the forward transform
+    x = rng.standard_normal(2000).astype(np.float32)
+    got = sep.stft(x, time_dim=0, size=256, shift=100)
+    want = oracle.stft(x, time_dim=0, size=256, shift=100)
+    assert got.shape == want.shape and rel_err(got, want) < TOL_REL
+
+
+def test_stft_unsupported_size_fails_loudly(sep):
+    with pytest.raises(NotImplementedError):
+        sep.stft(np.zeros(1000, np.float32), time_dim=0, size=200, shift=100)
+
+
+def test_stft_against_tfrecord_golden(sep, wsj0, tfrecord_golden):
+    """The reference's own committed STFT outputs (Blackman 256/128, audio zero
+    padded to 80000 samples -> 626 frames)."""
+    stride = int(tfrecord_golden["frame_stride"])
+    for i, utt in enumerate(wsj0):
+        pad = lambda x: np.pad(x, (0, 80000 - len(x)))
+        mix = pad(utt["mix"])[None]
+        refs = np.stack([pad(utt["s1"]), pad(utt["s2"])])[None]
+        feats, labels = sep.stft_features(mix, refs, size=256, shift=128)
+        assert feats.shape == (1, 626, 258) and labels.shape == (1, 626, 258)
+        g_in, g_lab = tfrecord_golden[f"inputs_{i}"], tfrecord_golden[f"labels_{i}"]
+        mag, ph = feats[0, ::stride, :129], feats[0, ::stride, 129:]
+        assert rel_err(mag, g_in[:, :129]) < TOL_REL
+        assert rel_err(labels[0, ::stride], g_lab) < TOL_REL
+        # phase is ill-conditioned where |X| ~ 0: compare it weighted by magnitude
+        dphi = np.angle(np.exp(1j * (ph.astype(np.float64) - g_in[:, 129:])))
+        assert np.max(np.abs(dphi) * g_in[:, :129]) < TOL_REL * np.max(g_in[:, :129])
+        full_mag = feats[0, :, :129].astype(np.float64)
+        chk = tfrecord_golden[f"checksum_{i}"]
+        assert abs(full_mag.sum() - chk[0]) < 1e-5 * abs(chk[0])
+        assert abs((labels[0].astype(np.float64) ** 2).sum() - chk[3]) < 1e-5 * abs(chk[3])
+        # frame count of the unpadded utterance = the `length` feature
+        assert sep.get_plan(256, 128).frames(len(utt["mix"])) == int(tfrecord_golden[f"length_{i}"])
+
+
+# ----------------------------------------------------------------- a7 / a8 istft
+@pytest.mark.parametrize("key", list(CONFIGS))
+def test_istft_matches_reference_run(sep, reference_run, key):
+    cfg = CONFIGS[key]
+    synth = sep._biorthogonal_window_loopy(cfg["window"](cfg["size"]), cfg["shift"])
+    assert np.max(np.abs(synth - reference_run[f"synth_{key}"])) < 1e-15
+    spec = reference_run[f"randspec_{key}"]
+    got = sep.istft(spec, **cfg)
+    want = reference_run[f"istft_rand_{key}"]
+    assert got.shape == want.shape and got.dtype == np.float64
+    assert rel_err(got, want) < TOL_REL and rel_l2(got, want) < TOL_L2
+    got = sep.istft(reference_run[f"stft_{key}"], **cfg)
+    assert rel_err(got, reference_run[f"istft_of_stft_{key}"]) < TOL_REL
+
+
+def test_istft_window_length_and_nofade(sep, oracle, reference_run):
+    got = sep.istft(reference_run["stft_winlen200"], size=256, shift=128, window_length=200)
+    assert rel_err(got, reference_run["istft_winlen200"]) < TOL_REL
+    rng = np.random.default_rng(3)
+    spec = rng.standard_normal((9, 129)) + 1j * rng.standard_normal((9, 129))
+    got = sep.istft(spec, size=256, shift=64, fading=False)
+    want = oracle.istft(spec, size=256, shift=64, fading=False)
+    assert got.shape == want.shape and rel_err(got, want) < TOL_REL
+
+
+def test_round_trip_on_committed_wavs(sep, oracle, wsj0):
+    """BASELINE config 1: STFT -> iSTFT round trip + SI-SNR on the test_wav files
+    (Hann 256/64) and the reference default (Blackman 256/128).  Round-trip
+    SI-SNR is a rounding-noise floor: assert >= 100 dB, not 0.01 dB."""
+    for cfg in (CONFIGS["hann_256_64"], CONFIGS["blackman_256_128"]):
+        for utt in wsj0:
+            for key in ("est_s1", "est_s2"):
+                x = utt[key]
+                y = sep.istft(sep.stft(x, time_dim=0, **cfg), **cfg)[:len(x)]
+                assert rel_err(y, x) < TOL_REL
+                snr = oracle.si_sdr(x.astype(np.float64), y.astype(np.float64))
+                assert snr > 100.0, snr
+
+
+def test_recombine_istft(sep, oracle):
+    rng = np.random.default_rng(11)
+    x = (0.1 * rng.standard_normal((2, 4000))).astype(np.float32)
+    cfg = CONFIGS["blackman_256_128"]
+    for b in range(2):
+        spec = oracle.stft(x[b], time_dim=0, **cfg)
+        if b == 0:
+            specs = np.empty((2,) + spec.shape, complex)
+        specs[b] = spec
+    mag, ph = np.abs(specs), np.angle(specs)
+    masks = rng.random((2, 2) + mag.shape[1:])
+    cleaned = np.concatenate([masks[:, 0] * mag, masks[:, 1] * mag], axis=-1)
+    got = sep.recombine_istft(cleaned.astype(np.float32), ph.astype(np.float32), 2, size=256, shift=128)
+    for b in range(2):
+        for c in range(2):
+            want = oracle.istft(oracle.recombine(cleaned[b, :, c * 129:(c + 1) * 129], ph[b]), **cfg)
+            assert rel_err(got[b, c], want) < TOL_REL
+
+
+# ----------------------------------------------------------------- a2 framing on device
+def test_segment_axis_device(sep, oracle):
+    import torch
+    a = np.arange(46, dtype=np.float32).reshape(2, 23)
+    for end in ("cut", "pad", "wrap"):
+        got = sep.segment_axis(torch.from_numpy(a).cuda(), 5, 2, axis=1, end=end, endvalue=-1)
+        want = oracle.segment_axis(a, 5, 2, axis=1, end=end, endvalue=-1)
+        assert np.array_equal(got.cpu().numpy(), want)
+
+
+# ----------------------------------------------------------------- a9 PIT-MSE
+def _pit_inputs(rng, batch, frames, feat, n_src, lengths):
+    labels = rng.standard_normal((batch, frames, n_src * feat)).astype(np.float32)
+    pred = np.abs(rng.standard_normal((batch, frames, n_src * feat))).astype(np.float32)
+    row = np.repeat(np.asarray(lengths, np.float32)[:, None, None], n_src * feat, axis=2)
+    return np.concatenate([labels, row], axis=1), pred
+
+
+@pytest.mark.parametrize("n_src,feat", [(2, 129), (2, 40), (3, 257), (1, 33), (4, 17)])
+def test_pit_mse(sep, oracle, n_src, feat):
+    rng = np.random.default_rng(100 + n_src)
+    batch, frames = 5, 61
+    y_true, y_pred = _pit_inputs(rng, batch, frames, feat, n_src, [61, 40, 1, 33, 60])
+    got = sep.pit_mse(y_true, y_pred, feat, with_grad=True)
+    want = oracle.pit_mse(y_true, y_pred, feat)
+    assert np.array_equal(got["idx"], want["idx"])                      # bit-exact permutation
+    assert np.allclose(got["pair"], want["pair"], rtol=TOL_LOSS)
+    assert np.allclose(got["costs"], want["costs"], rtol=TOL_LOSS)
+    assert abs(got["loss"] - want["loss"]) < TOL_LOSS * abs(want["loss"])
+    grad = oracle.pit_mse_grad(y_true, y_pred, feat)
+    assert np.allclose(got["grad"], grad, rtol=1e-5, atol=1e-7)
+    loss = sep.pit_with_outputsize(feat)(y_true, y_pred)
+    assert loss.dtype == np.float32 and abs(loss - want["loss"]) < 1e-5 * abs(want["loss"])
+
+
+def test_pit_permutation_semantics(sep, oracle):
+    rng = np.random.default_rng(7)
+    y_true, y_pred = _pit_inputs(rng, 6, 30, 129, 2, [30] * 6)
+    base = sep.pit_mse(y_true, y_pred, 129)
+    swapped = np.concatenate([y_pred[..., 129:], y_pred[..., :129]], axis=-1)
+    flip = sep.pit_mse(y_true, swapped, 129)
+    assert np.array_equal(flip["idx"], 1 - base["idx"])                 # equivariance
+    assert abs(flip["loss"] - base["loss"]) < 1e-9 * abs(base["loss"])
+    # exact tie -> perm 0 (strict `cost1 > cost2`, cell 28 :1054)
+    tie = np.concatenate([y_pred[..., :129], y_pred[..., :129]], axis=-1)
+    res = sep.pit_mse(y_true, tie, 129)
+    assert np.array_equal(res["idx"], np.zeros(6, np.int32))
+    assert np.array_equal(res["costs"][:, 0], res["costs"][:, 1])
+    # pred == labels -> zero loss
+    zero = sep.pit_mse(y_true, y_true[:, :-1], 129)
+    assert zero["loss"] == 0.0
+
+
+def test_pit_kats_on_golden_utterances(sep, oracle, wsj0):
+    """PIT-MSE known answers on the 4 golden utterances."""
+    pad = lambda x: np.pad(x, (0, 80000 - len(x)))
+    mix = np.stack([pad(u["mix"]) for u in wsj0])
+    refs = np.stack([np.stack([pad(u["s1"]), pad(u["s2"])]) for u in wsj0])
+    feats, labels = sep.stft_features(mix, refs, size=256, shift=128)
+    lengths = np.array([583, 443, 417, 384], np.float32)
+    y_true = np.concatenate([labels, np.repeat(lengths[:, None, None], 258, axis=2)], axis=1)
+    mag = feats[..., :129]
+    t, f = np.meshgrid(np.arange(626), np.arange(129), indexing="ij")
+    m1 = (0.25 + 0.5 * ((t + f) % 2)).astype(np.float32)
+    pred = np.concatenate([mag * m1, mag * (1 - m1)], axis=-1)
+    res = sep.pit_mse(y_true, pred, 129)
+    assert np.array_equal(res["idx"], [1, 1, 1, 1])
+    assert np.allclose(res["costs"][:, 0], [48.36308126, 53.58201924, 58.85509201, 40.4013118], rtol=1e-5)
+    assert np.allclose(res["costs"][:, 1], [48.21039997, 53.33102515, 58.65146917, 40.16040931], rtol=1e-5)
+    assert abs(res["loss"] - 200.3533036) < 1e-5 * 200.3533036
+    res = sep.pit_mse(y_true, np.concatenate([mag * 0.5, mag * 0.5], axis=-1), 129)
+    assert np.array_equal(res["idx"], [0, 0, 0, 0]) and abs(res["loss"] - 157.2335713) < 2e-3
+
+
+# ----------------------------------------------------------------- a10-a13 scoring
+def test_si_sdr_kats_on_committed_pairs(sep, wsj0, reference_run):
+    """The reference's own si_sdr / permute_si_sdr on tt/s{1,2} vs test_wav."""
+    table = reference_run["si_sdr_table"]
+    refs, ests = [], []
+    for utt in wsj0:
+        r1, r2, e1, e2 = sep.truncate_to_min_len(utt["s1"], utt["s2"], utt["est_s1"], utt["est_s2"])
+        refs.append([r1, r2])
+        ests.append([e1, e2])
+    res = sep.score_batch(refs, ests, 2)
+    for b in range(4):
+        assert len(refs[b][0]) == int(table[b, 5])
+        pair = res["si_pair"][b]            # [est i][ref j]
+        assert abs(pair[0, 0] - table[b, 0]) < TOL_DB and abs(pair[1, 1] - table[b, 1]) < TOL_DB
+        assert abs(pair[1, 0] - table[b, 2]) < TOL_DB and abs(pair[0, 1] - table[b, 3]) < TOL_DB
+        assert abs(res["si_best"][b] - table[b, 4]) < TOL_DB
+        assert res["si_perm"][b] == 0
+        assert abs(sep.permute_si_sdr(refs[b][0], refs[b][1], ests[b][0], ests[b][1]) - table[b, 4]) < TOL_DB
+        assert abs(sep.si_sdr(refs[b][0], ests[b][0]) - table[b, 0]) < TOL_DB
+    mean = np.mean(np.array([np.float32(v) for v in res["si_best"]]))
+    assert abs(mean - float(reference_run["si_sdr_mean"])) < TOL_DB
+    assert abs(res["sums"][0] / res["sums"][2] - float(reference_run["si_sdr_mean"])) < TOL_DB
+
+
+def test_score_batch_ragged_vs_oracle(sep, oracle):
+    rng = np.random.default_rng(42)
+    refs, ests, want_si, want_perm, want_sdr, want_sdr_perm = [], [], [], [], [], []
+    for b in range(12):
+        n = int(rng.integers(1, 30000)) if b else 8192 * 2   # include an exact chunk multiple
+        r = (0.1 * rng.standard_normal((2, n))).astype(np.float32)
+        snr = rng.uniform(-5, 20)
+        e = (r + 10 ** (-snr / 20) * 0.1 * rng.standard_normal((2, n))).astype(np.float32)
+        if b % 2:
+            e = e[::-1].copy()
+        refs.append(r)
+        ests.append(e)
+        v, p, _, _ = oracle.permute_si_sdr_detail(r[0], r[1], e[0], e[1])
+        want_si.append(v)
+        want_perm.append(p)
+        v, p, _, _ = oracle.permute_sdr_detail(r[0], r[1], e[0], e[1])
+        want_sdr.append(v)
+        want_sdr_perm.append(p)
+    res = sep.score_batch(refs, ests, 2)
+    ok = np.isfinite(want_si)
+    assert np.array_equal(np.asarray(res["si_perm"])[ok], np.asarray(want_perm)[ok])
+    assert np.max(np.abs(np.asarray(res["si_best"])[ok] - np.asarray(want_si)[ok])) < TOL_DB
+    assert np.array_equal(res["sdr_perm"][ok], np.asarray(want_sdr_perm)[ok])
+    assert np.max(np.abs(res["sdr_best"][ok] - np.asarray(want_sdr)[ok])) < TOL_DB
+
+
+def test_si_sdr_properties(sep):
+    rng = np.random.default_rng(9)
+    r = rng.standard_normal(5000).astype(np.float32)
+    e = (r + 0.3 * rng.standard_normal(5000)).astype(np.float32)
+    base = float(sep.si_sdr(r, e))
+    assert abs(float(sep.si_sdr(r, 7.5 * e)) - base) < 1e-4          # scale invariance
+    assert abs(float(sep.pow_np_norm(r)) - float(np.sum(r.astype(np.float64) ** 2))) < 1e-3
+    assert abs(float(sep.pow_norm(r, e)) - float(np.sum(r.astype(np.float64) * e))) < 1e-3
+
+
+# ----------------------------------------------------------------- fused hot path
+def _fused_case(rng, batch, n, n_src, cfg, oracle, ragged=False):
+    refs = (0.1 * rng.standard_normal((batch, n_src, n))).astype(np.float32)
+    mix = refs.sum(axis=1).astype(np.float32)
+    size, shift = cfg["size"], cfg["shift"]
+    frames = oracle.samples_to_stft_frames(n + 2 * (size - shift), size, shift)
+    masks = rng.random((batch, n_src, frames, size // 2 + 1)).astype(np.float32)
+    lengths = rng.integers(frames // 2, frames + 1, size=batch).astype(np.float32) if ragged else None
+    return mix, refs, masks, lengths
+
+
+@pytest.mark.parametrize("key,n_src,n", [
+    ("blackman_256_128", 2, 6000), ("hann_256_64", 2, 5000), ("hann_512_128", 3, 9000),
+    ("hamming_128_32", 1, 3001), ("blackman_256_128", 4, 2500), ("blackman_1024_256", 2, 12000),
+])
+def test_fused_matches_oracle(sep, oracle, key, n_src, n):
+    cfg = CONFIGS[key]
+    rng = np.random.default_rng(sum(map(ord, key)) + n_src)
+    mix, refs, masks, lengths = _fused_case(rng, 3, n, n_src, cfg, oracle, ragged=True)
+    res = sep.separate_and_score(mix, masks, refs, frame_lengths=lengths, **cfg)
+    for b in range(3):
+        want = oracle.separate_and_score(mix[b], refs[b], masks[b], length=lengths[b], **cfg)
+        assert rel_err(res["est"][b], want["ests"][:, :n]) < TOL_REL
+        assert rel_l2(res["est"][b], want["ests"][:, :n]) < 1e-5
+        pit = want["pit"]
+        assert int(res["pit_perm"][b]) == int(pit["idx"][0])            # bit-exact permutation
+        assert np.allclose(res["pit_pair"][b], pit["pair"][0], rtol=1e-4)
+        assert abs(res["pit_loss"][b] - pit["loss"]) < 1e-4 * abs(pit["loss"])
+        assert np.max(np.abs(res["si_pair"][b] - want["si_sdr_pair"])) < TOL_DB
+    assert abs(res["sums"][0] - res["pit_loss"].sum()) < 1e-9 * abs(res["sums"][0])
+    assert res["sums"][3] == 3
+
+
+def test_fused_est_only_and_identity_mask(sep, oracle):
+    """mask == 1 for a single source: est must reproduce the mixture (perfect reconstruction)."""
+    rng = np.random.default_rng(1)
+    cfg = CONFIGS["blackman_256_128"]
+    mix, refs, masks, _ = _fused_case(rng, 2, 32000, 1, cfg, oracle)
+    res = sep.separate_and_score(mix, np.ones_like(masks), None, **cfg)
+    assert rel_err(res["est"][:, 0], mix) < TOL_REL
+    assert oracle.si_sdr(mix[0].astype(np.float64), res["est"][0, 0].astype(np.float64)) > 100.0
+
+
+def test_fused_device_tensors_full_size(sep, oracle):
+    """BASELINE config 2 at full size (64 x 4 s, C=2), device-resident tensors;
+    checked through size-independent properties + a few utterances vs the oracle."""
+    import torch
+    rng = np.random.default_rng(2)
+    cfg = CONFIGS["blackman_256_128"]
+    mix, refs, masks, _ = _fused_case(rng, 64, 32000, 2, cfg, oracle)
+    dm, dr, dk = (torch.from_numpy(a).cuda() for a in (mix, refs, masks))
+    res = sep.separate_and_score(dm, dk, dr, **cfg)
+    torch.cuda.synchronize()
+    est = res["est"].cpu().numpy()
+    # linearity: masks m and 1 - m -> the two estimates sum to the mixture
+    comp = dk.clone()
+    comp[:, 1] = 1.0 - comp[:, 0]
+    res2 = sep.separate_and_score(dm, comp, dr, **cfg)
+    both = res2["est"].sum(dim=1).cpu().numpy()
+    assert rel_err(both, mix) < TOL_REL
+    for b in (0, 31, 63):
+        want = oracle.separate_and_score(mix[b], refs[b], masks[b], **cfg)
+        assert rel_err(est[b], want["ests"][:, :32000]) < TOL_REL
+        assert int(res["pit_perm"][b].item()) == int(want["pit"]["idx"][0])
+        assert abs(res["pit_loss"][b].item() - want["pit"]["loss"]) < 1e-4 * abs(want["pit"]["loss"])
+        assert np.max(np.abs(res["si_pair"][b].cpu().numpy() - want["si_sdr_pair"])) < TOL_DB
+    # host-pointer mode gives the same numbers as device-pointer mode
+    host = sep.separate_and_score(mix[:4], masks[:4], refs[:4], **cfg)
+    assert np.array_equal(host["est"], est[:4])
+    assert np.array_equal(host["scores"], res["scores"][:4].cpu().numpy())
+
+
+# ----------------------------------------------------------------- a14 conv1d filterbank
+def test_conv1d_reference_shape(sep, oracle):
+    """Raw_with_Convlayer: [B, K, 40] -> Conv1D(129, 2, sigmoid, 'same') (10449 params)."""
+    import torch
+    rng = np.random.default_rng(13)
+    x = rng.standard_normal((3, 97, 40)).astype(np.float32) * 0.1
+    w = (0.05 * rng.standard_normal((2, 40, 129))).astype(np.float32)
+    bias = (0.05 * rng.standard_normal(129)).astype(np.float32)
+    assert w.size + bias.size == 10449
+    got = sep.conv1d(x, w, bias, padding="same", activation="sigmoid")
+    want = oracle.conv1d(x, w, bias, padding="same", activation="sigmoid")
+    assert got.shape == (3, 97, 129) and np.max(np.abs(got - want)) < 1e-5
+    # independent formulation: torch conv1d on CPU, right padding by one row
+    xt = torch.from_numpy(np.pad(x, ((0, 0), (0, 1), (0, 0)))).permute(0, 2, 1)
+    wt = torch.from_numpy(w).permute(2, 1, 0)
+    ref = torch.sigmoid(torch.nn.functional.conv1d(xt, wt, torch.from_numpy(bias))).permute(0, 2, 1)
+    assert np.max(np.abs(got - ref.numpy())) < 1e-5
+
+
+@pytest.mark.parametrize("stride,padding,taps,act", [(1, "valid", 3, "relu"), (2, "same", 5, None),
+                                                      (8, "valid", 16, "relu")])
+def test_conv1d_variants(sep, oracle, stride, padding, taps, act):
+    rng = np.random.default_rng(taps)
+    c_in = 1 if taps == 16 else 7
+    x = rng.standard_normal((2, 333, c_in)).astype(np.float32)
+    w = rng.standard_normal((taps, c_in, 70)).astype(np.float32) * 0.2
+    got = sep.conv1d(x, w, None, stride=stride, padding=padding, activation=act)
+    want = oracle.conv1d(x, w, None, stride=stride, padding=padding, activation=act)
+    assert got.shape == want.shape and np.max(np.abs(got - want)) < 2e-5
