@@ -63,6 +63,14 @@ const char *sep_last_error(void);
  * (all threads); bench.py reports the difference over the timed region. */
 int64_t     sep_launch_count(void);
 
+/* Per-kernel timing for bench.py's roofline leg: while enabled, entry points
+ * bracket their dominant kernel with CUDA events on the launching stream (not
+ * during stream capture).  sep_profile_collect synchronises on the recorded
+ * events, returns the summed kernel time and the number of bracketed launches,
+ * and resets the log. */
+int sep_profile_enable(int on);
+int sep_profile_collect(double *total_ms, int *launches);
+
 /* ---- plan: window, twiddles, frame geometry ---------------------------- */
 /* `window` holds `size` float64 taps: the host evaluates the reference's
  * window callable (scipy, sym=True), including the window_length zero padding
@@ -150,6 +158,18 @@ int sep_fused_separate_f32(const sep_plan *plan, const float *mix, const float *
                            const int32_t *valid_samples, int batch, int n_src,
                            int64_t n_samples, float *est, double *scores, double *sums,
                            int mem, void *stream);
+
+/* As sep_fused_separate_f32, with caller-provided device scratch so that no
+ * allocation happens inside the call (CUDA-graph capture, steady-state
+ * serving).  workspace must hold sep_fused_workspace_bytes() bytes of device
+ * memory; only meaningful with SEP_MEM_DEVICE (host mode ignores it). */
+int sep_fused_workspace_bytes(const sep_plan *plan, int batch, int n_src, int64_t n_samples,
+                              int64_t *bytes);
+int sep_fused_separate_ws_f32(const sep_plan *plan, const float *mix, const float *masks,
+                              const float *refs, const float *frame_lengths,
+                              const int32_t *valid_samples, int batch, int n_src,
+                              int64_t n_samples, float *est, double *scores, double *sums,
+                              void *workspace, int64_t workspace_bytes, int mem, void *stream);
 
 /* ---- a9: pit_loss (uPIT_baseline.ipynb:1023-1059, cell 28) ------------- */
 /* y_true [batch, T+1, C*F] (last time row = valid length), y_pred [batch, T, C*F]

@@ -35,6 +35,9 @@ extern std::atomic<int64_t> g_launches;
     }                                                                               \
   } while (0)
 
+void profile_begin(cudaStream_t stream);
+void profile_end(cudaStream_t stream);
+
 // counts one kernel launch and checks the launch error
 #define SEP_LAUNCHED()                                                              \
   do {                                                                              \
@@ -75,15 +78,33 @@ namespace sep {
 struct Scratch {
   cudaStream_t stream;
   std::vector<void *> blocks;
+  // optional caller-provided arena (no allocation inside the call: CUDA graphs)
+  unsigned char *arena = nullptr;
+  size_t arena_bytes = 0, arena_used = 0;
   explicit Scratch(cudaStream_t s) : stream(s) {}
   ~Scratch() {
     for (void *p : blocks) cudaFreeAsync(p, stream);
+  }
+  void use_arena(void *base, size_t bytes) {
+    arena = static_cast<unsigned char *>(base);
+    arena_bytes = bytes;
+    arena_used = 0;
   }
   template <typename T>
   int alloc(T **out, size_t count) {
     void *p = nullptr;
     size_t bytes = count * sizeof(T);
     if (bytes == 0) bytes = sizeof(T);
+    if (arena) {
+      const size_t start = (arena_used + 255) & ~size_t(255);
+      if (start + bytes > arena_bytes) {
+        set_error("workspace too small: need %zu bytes, have %zu", start + bytes, arena_bytes);
+        return SEP_ERR_INVALID;
+      }
+      arena_used = start + bytes;
+      *out = reinterpret_cast<T *>(arena + start);
+      return SEP_OK;
+    }
     cudaError_t e = cudaMallocAsync(&p, bytes, stream);
     if (e != cudaSuccess) {
       set_error("cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));

@@ -285,7 +285,9 @@ static int run_fused(const sep_plan *p, FusedArgs a, int batch, double *d_scores
                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(cfg.smem)));
   dim3 grid(a.tiles, batch);
+  profile_begin(stream);
   fused_generic_kernel<C><<<grid, cfg.warps * 32, cfg.smem, stream>>>(a);
+  profile_end(stream);
   SEP_LAUNCHED();
   if (score) {
     const int stride = sep_score_stride(C);
@@ -308,11 +310,34 @@ static int run_fused(const sep_plan *p, FusedArgs a, int batch, double *d_scores
 
 using namespace sep;
 
+extern "C" int sep_fused_workspace_bytes(const sep_plan *p, int batch, int n_src, int64_t n_samples,
+                                         int64_t *bytes) {
+  SEP_REQUIRE(p && bytes, "sep_fused_workspace_bytes: null argument");
+  SEP_REQUIRE(n_src >= 1 && n_src <= SEP_MAX_SOURCES && batch >= 1 && n_samples >= 1,
+              "sep_fused_workspace_bytes: bad shape");
+  int T = 0;
+  sep_plan_frames(p, n_samples, &T);
+  // worst case: one tile per frame, NV doubles per tile, plus alignment slack
+  const int64_t nv = 2 * n_src * n_src + 2 * n_src;
+  *bytes = static_cast<int64_t>(batch) * T * nv * 8 + 4096;
+  return SEP_OK;
+}
+
 extern "C" int sep_fused_separate_f32(const sep_plan *p, const float *mix, const float *masks,
                                       const float *refs, const float *frame_lengths,
                                       const int32_t *valid_samples, int batch, int n_src,
                                       int64_t n_samples, float *est, double *scores, double *sums,
-                                      int mem, void *stream_) {
+                                      int mem, void *stream) {
+  return sep_fused_separate_ws_f32(p, mix, masks, refs, frame_lengths, valid_samples, batch, n_src,
+                                   n_samples, est, scores, sums, nullptr, 0, mem, stream);
+}
+
+extern "C" int sep_fused_separate_ws_f32(const sep_plan *p, const float *mix, const float *masks,
+                                         const float *refs, const float *frame_lengths,
+                                         const int32_t *valid_samples, int batch, int n_src,
+                                         int64_t n_samples, float *est, double *scores,
+                                         double *sums, void *workspace, int64_t workspace_bytes,
+                                         int mem, void *stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SEP_REQUIRE(p && mix && masks, "sep_fused_separate_f32: null argument");
   SEP_REQUIRE(n_src >= 1 && n_src <= SEP_MAX_SOURCES, "sep_fused_separate_f32: n_src=%d out of range",
@@ -331,6 +356,7 @@ extern "C" int sep_fused_separate_f32(const sep_plan *p, const float *mix, const
   sep_plan_frames(p, n_samples, &T);
   const int C = n_src, stride = sep_score_stride(C);
   Scratch s(stream);
+  if (workspace && mem == SEP_MEM_DEVICE) s.use_arena(workspace, static_cast<size_t>(workspace_bytes));
   FusedArgs a{};
   const size_t wave_count = static_cast<size_t>(batch) * n_samples;
   const size_t mask_count = static_cast<size_t>(batch) * C * T * p->bins;

@@ -20,6 +20,28 @@ void set_error(const char *fmt, ...) {
   t_error = buf;
 }
 
+// Optional per-kernel timing: when enabled, entry points bracket their dominant
+// kernel with CUDA events on the launching stream (bench.py's roofline leg).
+static std::mutex g_prof_mutex;
+static bool g_prof_on = false;
+static std::vector<cudaEvent_t> g_prof_events;   // begin/end pairs
+static size_t g_prof_used = 0;
+
+static void profile_mark(cudaStream_t stream) {
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  if (!g_prof_on) return;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return;
+  if (g_prof_used == g_prof_events.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    g_prof_events.push_back(e);
+  }
+  cudaEventRecord(g_prof_events[g_prof_used++], stream);
+}
+void profile_begin(cudaStream_t stream) { profile_mark(stream); }
+void profile_end(cudaStream_t stream) { profile_mark(stream); }
+
 template <typename T>
 static int upload(T **dst, const std::vector<T> &host) {
   SEP_CUDA(cudaMalloc(reinterpret_cast<void **>(dst), host.size() * sizeof(T)));
@@ -38,6 +60,31 @@ int sep_version(void) { return 100; }
 const char *sep_last_error(void) { return t_error.c_str(); }
 
 int64_t sep_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int sep_profile_enable(int on) {
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  g_prof_on = on != 0;
+  g_prof_used = 0;
+  return SEP_OK;
+}
+
+int sep_profile_collect(double *total_ms, int *launches) {
+  SEP_REQUIRE(total_ms && launches, "sep_profile_collect: null argument");
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  double total = 0.0;
+  int count = 0;
+  for (size_t i = 0; i + 1 < g_prof_used; i += 2) {
+    SEP_CUDA(cudaEventSynchronize(g_prof_events[i + 1]));
+    float ms = 0.f;
+    SEP_CUDA(cudaEventElapsedTime(&ms, g_prof_events[i], g_prof_events[i + 1]));
+    total += ms;
+    ++count;
+  }
+  *total_ms = total;
+  *launches = count;
+  g_prof_used = 0;
+  return SEP_OK;
+}
 
 int sep_plan_create(sep_plan **out, int size, int shift, const double *window, int fading) {
   SEP_REQUIRE(out != nullptr && window != nullptr, "sep_plan_create: null argument");

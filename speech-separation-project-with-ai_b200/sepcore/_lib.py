@@ -37,6 +37,8 @@ PROTOTYPES = {
     "sep_version": (_int, []),
     "sep_last_error": (C.c_char_p, []),
     "sep_launch_count": (_i64, []),
+    "sep_profile_enable": (_int, [_int]),
+    "sep_profile_collect": (_int, [_f64p, C.POINTER(_int)]),
     "sep_plan_create": (_int, [C.POINTER(_vp), _int, _int, _f64p, _int]),
     "sep_plan_destroy": (_int, [_vp]),
     "sep_plan_frames": (_int, [_vp, _i64, C.POINTER(_int)]),
@@ -50,6 +52,9 @@ PROTOTYPES = {
     "sep_recombine_istft_f32": (_int, [_vp, _vp, _vp, _int, _int, _int, _vp, _int, _vp]),
     "sep_fused_separate_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _i64, _vp, _vp,
                                       _vp, _int, _vp]),
+    "sep_fused_workspace_bytes": (_int, [_vp, _int, _int, _i64, C.POINTER(_i64)]),
+    "sep_fused_separate_ws_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _i64, _vp, _vp,
+                                         _vp, _vp, _i64, _int, _vp]),
     "sep_pit_mse_f32": (_int, [_vp, _vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "sep_score_batch_f32": (_int, [_vp, _vp, _i64p, _i64p, _i64p, _int, _int, _i64, _i64, _vp, _vp,
                                    _int, _vp]),
@@ -95,3 +100,14 @@ def check(rc, what=""):
 
 def launch_count():
     return int(load().sep_launch_count())
+
+
+def profile_enable(on=True):
+    check(load().sep_profile_enable(1 if on else 0), "sep_profile_enable")
+
+
+def profile_collect():
+    """(total kernel ms, bracketed launches) since the last call; resets the log."""
+    total, count = C.c_double(), C.c_int()
+    check(load().sep_profile_collect(C.byref(total), C.byref(count)), "sep_profile_collect")
+    return total.value, count.value

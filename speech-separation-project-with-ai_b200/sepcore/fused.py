@@ -43,8 +43,19 @@ def parse_scores(scores, n_src):
     return out
 
 
+def workspace_bytes(batch, n_src, n_samples, size=256, shift=128, window=None):
+    """Device scratch needed by one fused call (see `workspace=` below)."""
+    import ctypes as C
+
+    plan = get_plan(size, shift, window, True)
+    out = C.c_int64()
+    _lib.check(_lib.load().sep_fused_workspace_bytes(plan.handle, int(batch), int(n_src),
+                                                     int(n_samples), C.byref(out)))
+    return out.value
+
+
 def separate_and_score(mix, masks, refs=None, frame_lengths=None, valid_samples=None,
-                       size=256, shift=128, window=None, want_est=True, out=None):
+                       size=256, shift=128, window=None, want_est=True, out=None, workspace=None):
     """One fused pass.
 
     mix [B, N] float32; masks [B, C, T, F] float32 with T = frames(N), F = size/2+1;
@@ -54,7 +65,10 @@ def separate_and_score(mix, masks, refs=None, frame_lengths=None, valid_samples=
     Returns dict: est [B, C, N] (if want_est), and when refs are given the parsed
     per-utterance scores plus `sums` = [sum pit_loss, sum si_best, sum sdr_best, B].
     numpy in -> numpy out (library stages copies); CUDA tensors in -> CUDA tensors out.
-    `out` may carry preallocated 'est' / 'scores' / 'sums' buffers (device mode).
+    `out` may carry preallocated 'est' / 'scores' / 'sums' buffers (CUDA tensors in
+    device mode; numpy arrays -- e.g. views of pinned memory -- in host mode).
+    `workspace` (device mode): a uint8 CUDA tensor of `workspace_bytes(...)` bytes;
+    with it the call allocates nothing, so it can be captured into a CUDA graph.
     """
     plan = get_plan(size, shift, window, True)
     lib = _lib.load()
@@ -102,14 +116,28 @@ def separate_and_score(mix, masks, refs=None, frame_lengths=None, valid_samples=
                 sums = torch.empty((4,), dtype=torch.float64, device=m.device)
     else:
         if want_est:
-            est = np.empty((batch, n_src, n), dtype=np.float32)
+            est = out.get("est")
+            if est is None:
+                est = np.empty((batch, n_src, n), dtype=np.float32)
         if r is not None:
-            scores = np.empty((batch, stride), dtype=np.float64)
-            sums = np.empty((4,), dtype=np.float64)
-    _lib.check(lib.sep_fused_separate_f32(plan.handle, ptr(m), ptr(k), ptr(r), ptr(fl), ptr(vs), batch,
-                                          n_src, n, ptr(est), ptr(scores), ptr(sums), mem,
-                                          current_stream(mem, m if dev else None)),
-               "sep_fused_separate_f32")
+            scores = out.get("scores")
+            if scores is None:
+                scores = np.empty((batch, stride), dtype=np.float64)
+            sums = out.get("sums")
+            if sums is None:
+                sums = np.empty((4,), dtype=np.float64)
+    for name, buf, shape in (("est", est, (batch, n_src, n)), ("scores", scores, (batch, stride)),
+                             ("sums", sums, (4,))):
+        if buf is not None and tuple(int(v) for v in buf.shape) != shape:
+            raise ValueError("out[%r] must have shape %r" % (name, shape))
+    ws_ptr, ws_bytes = None, 0
+    if workspace is not None and dev:
+        ws_ptr, ws_bytes = ptr(workspace), int(workspace.numel() * workspace.element_size())
+    _lib.check(lib.sep_fused_separate_ws_f32(plan.handle, ptr(m), ptr(k), ptr(r), ptr(fl), ptr(vs),
+                                             batch, n_src, n, ptr(est), ptr(scores), ptr(sums),
+                                             ws_ptr, ws_bytes, mem,
+                                             current_stream(mem, m if dev else None)),
+               "sep_fused_separate_ws_f32")
     res = {}
     if want_est:
         res["est"] = est
