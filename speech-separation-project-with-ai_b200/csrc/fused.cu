@@ -200,48 +200,6 @@ __global__ void __launch_bounds__(256) fused_generic_kernel(const FusedArgs a) {
   }
 }
 
-// One warp per utterance: sums the tile partials in tile order, then the
-// permutation searches.  scores row layout: see sepcore.h.
-template <int C>
-__global__ void fused_finalize_kernel(const double *__restrict__ partials, int tiles,
-                                      const float *__restrict__ lengths, int T,
-                                      double *__restrict__ scores, int stride) {
-  constexpr int NV = FusedVals<C>::NV;
-  constexpr int P = (C == 1) ? 1 : (C == 2) ? 2 : (C == 3) ? 6 : 24;
-  const int b = blockIdx.x, lane = threadIdx.x;
-  double v[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) v[i] = 0.0;
-  for (int t = lane; t < tiles; t += 32) {
-    const double *src = partials + (static_cast<int64_t>(b) * tiles + t) * NV;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] += src[i];
-  }
-#pragma unroll
-  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
-  if (lane == 0) {
-    double *row = scores + static_cast<int64_t>(b) * stride;
-    const double len = lengths ? static_cast<double>(lengths[b]) : static_cast<double>(T);
-    finalize_pit<C>(v, len, row);
-    finalize_scores<C>(v + C * C, v + 2 * C * C, v + 2 * C * C + C, row + C * C + P + 2);
-  }
-}
-
-// sums[4] = {sum pit_loss, sum si_best, sum sdr_best, batch}; one warp, fixed order.
-__global__ void fused_sums_kernel(const double *__restrict__ scores, int batch, int stride,
-                                  int off_pit, int off_si, int off_sdr, double *__restrict__ sums) {
-  const int lane = threadIdx.x;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-  for (int b = lane; b < batch; b += 32) {
-    const double *row = scores + static_cast<int64_t>(b) * stride;
-    s0 += row[off_pit];
-    s1 += row[off_si];
-    s2 += row[off_sdr];
-  }
-  s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
-  if (lane == 0) { sums[0] = s0; sums[1] = s1; sums[2] = s2; sums[3] = batch; }
-}
-
 struct FusedCfg { int warps, tb; size_t smem; };
 
 static bool pick_fused(const sep_plan *p, int C, FusedCfg *out) {
@@ -289,20 +247,7 @@ static int run_fused(const sep_plan *p, FusedArgs a, int batch, double *d_scores
   fused_generic_kernel<C><<<grid, cfg.warps * 32, cfg.smem, stream>>>(a);
   profile_end(stream);
   SEP_LAUNCHED();
-  if (score) {
-    const int stride = sep_score_stride(C);
-    fused_finalize_kernel<C><<<batch, 32, 0, stream>>>(partials, a.tiles, a.lengths, a.T, d_scores,
-                                                       stride);
-    SEP_LAUNCHED();
-    if (d_sums) {
-      const int P = factorial(C);
-      const int off_pit = C * C + P + 1, off_si = C * C + P + 2 + C * C;
-      const int off_sdr = off_si + 2 + C * C;
-      fused_sums_kernel<<<1, 32, 0, stream>>>(d_scores, batch, stride, off_pit, off_si, off_sdr,
-                                              d_sums);
-      SEP_LAUNCHED();
-    }
-  }
+  if (score) return launch_fused_finalize<C>(a, batch, d_scores, d_sums, stream);
   return SEP_OK;
 }
 
@@ -378,6 +323,7 @@ extern "C" int sep_fused_separate_ws_f32(const sep_plan *p, const float *mix, co
   a.syn = p->d_syn;
   a.tw_half = p->d_tw_half;
   a.tw_full = p->d_tw_full;
+  a.tw16 = p->d_tw16;
 
   bool handled = false;
   if ((rc = fused_fast_try(p, a, batch, C, d_scores, d_sums, s, stream, &handled))) return rc;

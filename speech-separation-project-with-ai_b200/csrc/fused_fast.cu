@@ -1,15 +1,291 @@
-// fused_fast.cu -- register-resident specialisation of the fused hot path
-// (size 256 / 512).  Placeholder until the 16x16 register FFT lands: reports
-// "not handled" so the generic shared-memory kernel runs.
+// fused_fast.cu -- register-resident specialisation of the fused hot path for
+// size = 256 (shift 128 or 64), 1..4 sources.
+//
+// Same contract and tile decomposition as fused.cu (owned frames / recomputed
+// halo / float64 tile partials), but:
+//   * each half-warp transforms a PAIR of consecutive frames as one complex
+//     256-point FFT held in registers (fft256.cuh): frame t rides in the real
+//     part, frame t+1 in the imaginary part.  A frame pair costs 1 + C forward
+//     and C inverse complex transforms (mixture + C references, C estimates).
+//   * mask multiply, |X|, PSA labels and the PIT squared differences happen on
+//     the split spectra in registers;  spec_c = mask_c * X (cell 41 identity).
+//   * overlap-add is atomic-free and needs no frame buffer: windowed time
+//     frames are added straight into a shared accumulator in size/shift phases
+//     (frames with equal t mod size/shift never overlap), one __syncthreads
+//     between phases.
+// Reference lines: see fused.cu.
+#include <cstdlib>
+
 #include "common.cuh"
+#include "fft256.cuh"
 #include "fused.cuh"
 
 namespace sep {
 
-int fused_fast_try(const sep_plan *, const FusedArgs &, int, int, double *, double *, Scratch &,
-                   cudaStream_t, bool *handled) {
-  *handled = false;
+constexpr int kUnits = 8;                 // half-warps per CTA -> 128 threads
+constexpr int kFastThreads = kUnits * 16;
+
+template <int C, int R>
+struct FastGeom {
+  static constexpr int N = 256, SHIFT = N / R;
+  static constexpr int FRAMES = 2 * kUnits;            // frames transformed per tile
+  static constexpr int TB = FRAMES - (R - 1);          // owned frames / output hop-blocks
+  static constexpr int TILE = (FRAMES - 1) * SHIFT + N;   // staged samples == accumulator span
+  static constexpr int NV = FusedVals<C>::NV;
+  static constexpr size_t smem(bool score) {
+    return sizeof(float) * TILE * ((score ? 1 + C : 1) + C)   // wave tiles + accumulators
+         + sizeof(float2) * kXchFloat2 * kUnits               // transpose buffers (also reduction scratch)
+         + sizeof(float) * 2 * N;                             // analysis / synthesis windows
+  }
+};
+
+template <int C, int R, bool SCORE>
+__global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedArgs a) {
+  using G = FastGeom<C, R>;
+  constexpr int N = G::N, SHIFT = G::SHIFT, TILE = G::TILE, TB = G::TB;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float *tiles = reinterpret_cast<float *>(smem_raw);              // [1 (+C)][TILE]
+  float *acc = tiles + TILE * (SCORE ? 1 + C : 1);                 // [C][TILE]
+  float2 *xch_all = reinterpret_cast<float2 *>(acc + TILE * C);    // [kUnits][kXchFloat2]
+  float *win = reinterpret_cast<float *>(xch_all + kXchFloat2 * kUnits);   // [N] 0.5 * analysis
+  float *syn = win + N;                                            // [N] synthesis
+
+  const int T = a.T, b = blockIdx.y, tile = blockIdx.x;
+  const int own_lo = tile * TB, own_hi = min(own_lo + TB, T);
+  const int j0 = max(own_lo, R - 1), j1 = own_hi;                  // output hop-blocks
+  const int t_lo = max(own_lo - (R - 1), 0);                       // first frame transformed
+  const int64_t s0 = static_cast<int64_t>(t_lo) * SHIFT - a.pad;   // original index of tile[0]
+  const int unit = threadIdx.x >> 4, l16 = threadIdx.x & 15;
+  float2 *xch = xch_all + unit * kXchFloat2;
+
+  // ---- stage waveforms (zeros outside [0, n)), clear accumulators, windows ----
+  constexpr int NSIG = SCORE ? 1 + C : 1;
+#pragma unroll
+  for (int sgn = 0; sgn < NSIG; ++sgn) {
+    const float *row = sgn == 0 ? a.mix + static_cast<int64_t>(b) * a.n
+                                : a.refs + (static_cast<int64_t>(b) * C + (sgn - 1)) * a.n;
+    float *dst = tiles + TILE * sgn;
+    const bool vec = ((reinterpret_cast<uintptr_t>(row + s0) & 15) == 0) && s0 >= 0 && s0 + TILE <= a.n;
+    if (vec) {
+      for (int i = threadIdx.x; i < TILE / 4; i += kFastThreads)
+        reinterpret_cast<float4 *>(dst)[i] = __ldg(reinterpret_cast<const float4 *>(row + s0) + i);
+    } else {
+      for (int i = threadIdx.x; i < TILE; i += kFastThreads) {
+        const int64_t g = s0 + i;
+        dst[i] = (g >= 0 && g < a.n) ? __ldg(row + g) : 0.f;
+      }
+    }
+  }
+  for (int i = threadIdx.x; i < TILE * C / 4; i += kFastThreads)
+    reinterpret_cast<float4 *>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = threadIdx.x; i < N; i += kFastThreads) {
+    win[i] = __ldg(a.win_half + i);
+    syn[i] = __ldg(a.syn + i);
+  }
+  float2 tw[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) tw[j] = __ldg(a.tw16 + l16 * 16 + j);
+  __syncthreads();
+
+  // ---- this half-warp's frame pair ----
+  const int f0 = 2 * unit, f1 = f0 + 1;                // local frame indices
+  const int ta = t_lo + f0, tb = t_lo + f1;            // global frame indices
+  float2 v[16];
+  float wl[16];
+#pragma unroll
+  for (int m = 0; m < 16; ++m) wl[m] = win[l16 + 16 * m];
+#pragma unroll
+  for (int m = 0; m < 16; ++m)
+    v[m] = make_float2(tiles[f0 * SHIFT + l16 + 16 * m] * wl[m], tiles[f1 * SHIFT + l16 + 16 * m] * wl[m]);
+  fft256<false>(v, tw, xch, l16);
+  float2 Xa[9], Xb[9];
+  split_pair(v, l16, Xa, Xb);
+
+  // masks of both frames at this lane's bins (coalesced 64-byte runs per row)
+  float ma[C][9], mb[C][9];
+#pragma unroll
+  for (int q = 0; q < C; ++q) {
+    const float *base = a.masks + (static_cast<int64_t>(b) * C + q) * T * 129;
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const bool bin_ok = r < 8 || l16 == 0;
+      ma[q][r] = (bin_ok && ta < T) ? __ldg(base + static_cast<int64_t>(ta) * 129 + l16 + 16 * r) : 0.f;
+      mb[q][r] = (bin_ok && tb < T) ? __ldg(base + static_cast<int64_t>(tb) * 129 + l16 + 16 * r) : 0.f;
+    }
+  }
+
+  float pit[C * C];
+#pragma unroll
+  for (int i = 0; i < C * C; ++i) pit[i] = 0.f;
+  if (SCORE) {
+    const float len_f = a.lengths ? a.lengths[b] : static_cast<float>(T);
+    const int len_i = static_cast<int>(len_f);
+    // weights: frame counted once (owned), prediction gated by t < length (cell 28 :1031-1046)
+    const float own_a = (ta >= own_lo && ta < own_hi) ? 1.f : 0.f;
+    const float own_b = (tb >= own_lo && tb < own_hi) ? 1.f : 0.f;
+    const float gate_a = ta < len_i ? 1.f : 0.f, gate_b = tb < len_i ? 1.f : 0.f;
+    float inv_a[9], inv_b[9], mag_a[9], mag_b[9];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const float pa = fmaf(Xa[r].x, Xa[r].x, Xa[r].y * Xa[r].y);
+      const float pb = fmaf(Xb[r].x, Xb[r].x, Xb[r].y * Xb[r].y);
+      inv_a[r] = pa > 0.f ? rsqrtf(pa) : 0.f;
+      inv_b[r] = pb > 0.f ? rsqrtf(pb) : 0.f;
+      mag_a[r] = pa * inv_a[r] * gate_a;
+      mag_b[r] = pb * inv_b[r] * gate_b;
+    }
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      const float *ref = tiles + TILE * (1 + j);
+#pragma unroll
+      for (int m = 0; m < 16; ++m)
+        v[m] = make_float2(ref[f0 * SHIFT + l16 + 16 * m] * wl[m], ref[f1 * SHIFT + l16 + 16 * m] * wl[m]);
+      fft256<false>(v, tw, xch, l16);
+      float2 Sa[9], Sb[9];
+      split_pair(v, l16, Sa, Sb);
+#pragma unroll
+      for (int r = 0; r < 9; ++r) {
+        const float bin_w = (r < 8 || l16 == 0) ? 1.f : 0.f;
+        // label = |S| cos(angle X - angle S) = Re(S conj X) / |X| ; angle(0) = 0 -> Re S
+        const float la = inv_a[r] > 0.f ? fmaf(Sa[r].x, Xa[r].x, Sa[r].y * Xa[r].y) * inv_a[r] : Sa[r].x;
+        const float lb = inv_b[r] > 0.f ? fmaf(Sb[r].x, Xb[r].x, Sb[r].y * Xb[r].y) * inv_b[r] : Sb[r].x;
+        const float wa = own_a * bin_w, wb = own_b * bin_w;
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+          const float da = fmaf(ma[i][r], mag_a[r], -la), db = fmaf(mb[i][r], mag_b[r], -lb);
+          pit[i * C + j] = fmaf(wa * da, da, pit[i * C + j]);
+          pit[i * C + j] = fmaf(wb * db, db, pit[i * C + j]);
+        }
+      }
+    }
+  }
+
+  // ---- masked spectra -> time frames -> phased overlap-add ----
+  float sl[16];
+#pragma unroll
+  for (int m = 0; m < 16; ++m) sl[m] = syn[l16 + 16 * m];
+#pragma unroll
+  for (int q = 0; q < C; ++q) {
+    float2 L[9], Mi[9];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      // P = m_a X_a (frame ta, real part), Q = m_b X_b (frame tb, imaginary part)
+      const float2 P = make_float2(ma[q][r] * Xa[r].x, ma[q][r] * Xa[r].y);
+      const float2 Q = make_float2(mb[q][r] * Xb[r].x, mb[q][r] * Xb[r].y);
+      L[r] = make_float2(P.x - Q.y, P.y + Q.x);       // P + i Q
+      Mi[r] = make_float2(P.x + Q.y, Q.x - P.y);      // conj P + i conj Q
+    }
+    merge_pair(v, l16, L, Mi);
+    fft256<true>(v, tw, xch, l16);
+    float *accq = acc + TILE * q;
+#pragma unroll
+    for (int ph = 0; ph < R; ++ph) {
+      if ((f0 % R) == ph) {
+#pragma unroll
+        for (int m = 0; m < 16; ++m) accq[f0 * SHIFT + l16 + 16 * m] += v[m].x * sl[m];
+      }
+      if ((f1 % R) == ph) {
+#pragma unroll
+        for (int m = 0; m < 16; ++m) accq[f1 * SHIFT + l16 + 16 * m] += v[m].y * sl[m];
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- write estimates, Gram partials ----
+  double gram[C * C], ee[C], er[C];
+#pragma unroll
+  for (int i = 0; i < C * C; ++i) gram[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < C; ++i) { ee[i] = 0.0; er[i] = 0.0; }
+  const int64_t n_valid = (SCORE && a.valid) ? min(static_cast<int64_t>(a.valid[b]), a.n) : a.n;
+  const int span = (j1 - j0) * SHIFT;
+  const int first = (j0 - t_lo) * SHIFT;                      // accumulator index of output sample 0
+  const int64_t g0 = static_cast<int64_t>(j0) * SHIFT - a.pad;   // its original sample index
+  for (int i = threadIdx.x; i < span; i += kFastThreads) {
+    const int64_t g = g0 + i;
+    if (g >= a.n) break;
+    float e[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      e[c] = acc[TILE * c + first + i];
+      if (a.est) a.est[(static_cast<int64_t>(b) * C + c) * a.n + g] = e[c];
+    }
+    if (SCORE && g < n_valid) {
+#pragma unroll
+      for (int jr = 0; jr < C; ++jr) {
+        const double r = static_cast<double>(tiles[TILE * (1 + jr) + first + i]);
+        er[jr] = fma(r, r, er[jr]);
+#pragma unroll
+        for (int ie = 0; ie < C; ++ie) gram[ie * C + jr] = fma(static_cast<double>(e[ie]), r, gram[ie * C + jr]);
+      }
+#pragma unroll
+      for (int ie = 0; ie < C; ++ie) {
+        const double x = static_cast<double>(e[ie]);
+        ee[ie] = fma(x, x, ee[ie]);
+      }
+    }
+  }
+  if (!SCORE) return;
+  constexpr int NV = G::NV;
+  double vals[NV];
+#pragma unroll
+  for (int i = 0; i < C * C; ++i) { vals[i] = static_cast<double>(pit[i]); vals[C * C + i] = gram[i]; }
+#pragma unroll
+  for (int i = 0; i < C; ++i) { vals[2 * C * C + i] = ee[i]; vals[2 * C * C + C + i] = er[i]; }
+  block_sum<NV>(vals, reinterpret_cast<double *>(xch_all));   // transpose buffers are idle now
+  if (threadIdx.x == 0) {
+    double *dst = a.partials + (static_cast<int64_t>(b) * a.tiles + tile) * NV;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) dst[i] = vals[i];
+  }
+}
+
+template <int C, int R, bool SCORE>
+static int launch_fast(FusedArgs a, int batch, double *d_scores, double *d_sums, Scratch &s,
+                       cudaStream_t stream) {
+  using G = FastGeom<C, R>;
+  a.tb = G::TB;
+  a.tiles = (a.T + G::TB - 1) / G::TB;
+  int rc;
+  double *partials = nullptr;
+  if (SCORE && (rc = s.alloc(&partials, static_cast<size_t>(batch) * a.tiles * G::NV))) return rc;
+  a.partials = partials;
+  const size_t smem = G::smem(SCORE);
+  SEP_CUDA(cudaFuncSetAttribute(fused256_kernel<C, R, SCORE>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  dim3 grid(a.tiles, batch);
+  profile_begin(stream);
+  fused256_kernel<C, R, SCORE><<<grid, kFastThreads, smem, stream>>>(a);
+  profile_end(stream);
+  SEP_LAUNCHED();
+  if (SCORE) return launch_fused_finalize<C>(a, batch, d_scores, d_sums, stream);
   return SEP_OK;
+}
+
+template <int C>
+static int dispatch_fast(const sep_plan *p, const FusedArgs &a, int batch, double *d_scores,
+                         double *d_sums, Scratch &s, cudaStream_t stream) {
+  const bool score = a.refs != nullptr;
+  if (p->hops == 2)
+    return score ? launch_fast<C, 2, true>(a, batch, d_scores, d_sums, s, stream)
+                 : launch_fast<C, 2, false>(a, batch, d_scores, d_sums, s, stream);
+  return score ? launch_fast<C, 4, true>(a, batch, d_scores, d_sums, s, stream)
+               : launch_fast<C, 4, false>(a, batch, d_scores, d_sums, s, stream);
+}
+
+int fused_fast_try(const sep_plan *p, const FusedArgs &a, int batch, int C, double *d_scores,
+                   double *d_sums, Scratch &s, cudaStream_t stream, bool *handled) {
+  *handled = false;
+  if (p->size != 256 || (p->hops != 2 && p->hops != 4)) return SEP_OK;
+  if (getenv("SEPCORE_FORCE_GENERIC")) return SEP_OK;
+  *handled = true;
+  switch (C) {
+    case 1: return dispatch_fast<1>(p, a, batch, d_scores, d_sums, s, stream);
+    case 2: return dispatch_fast<2>(p, a, batch, d_scores, d_sums, s, stream);
+    case 3: return dispatch_fast<3>(p, a, batch, d_scores, d_sums, s, stream);
+    default: return dispatch_fast<4>(p, a, batch, d_scores, d_sums, s, stream);
+  }
 }
 
 }  // namespace sep

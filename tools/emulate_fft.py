@@ -100,6 +100,83 @@ def ifft256_16x16(Y):
     return y
 
 
+def fft16_radix4(v, inverse=False):
+    """The in-register 16-point FFT of fft256.cuh (n = 4a + b, k = c + 4d)."""
+    v = list(v)
+    sgn = 1 if inverse else -1
+
+    def fft4(x0, x1, x2, x3):
+        t0, t1, t2, t3 = x0 + x2, x0 - x2, x1 + x3, x1 - x3
+        r = t3 * (1j if inverse else -1j)
+        return t0 + t2, t1 + r, t0 - t2, t1 - r
+
+    for b in range(4):
+        v[b], v[4 + b], v[8 + b], v[12 + b] = fft4(v[b], v[4 + b], v[8 + b], v[12 + b])
+    for c in range(1, 4):
+        for b in range(1, 4):
+            v[4 * c + b] *= np.exp(sgn * 2j * np.pi * b * c / 16)
+    for c in range(4):
+        v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3] = fft4(*v[4 * c:4 * c + 4])
+    out = [0] * 16
+    for c in range(4):
+        for d in range(4):
+            out[c + 4 * d] = v[4 * c + d]
+    return np.array(out)
+
+
+def lanes_split_pair(V):
+    """V[lane][k2] = Z[lane + 16 k2] -> A[lane][r], B[lane][r] (r = 0..8)."""
+    A = np.zeros((16, 9), complex); B = np.zeros((16, 9), complex)
+    for l in range(16):
+        src = (16 - l) & 15
+        for r in range(9):
+            got = V[src][15 - r if r < 8 else 7]
+            own = V[l][(16 - r) & 15]
+            zp = own if l == 0 else got
+            z = V[l][r]
+            A[l, r] = complex(z.real + zp.real, z.imag - zp.imag)
+            B[l, r] = complex(z.imag + zp.imag, zp.real - z.real)
+    return A, B
+
+
+def lanes_merge_pair(L, Mi):
+    V = np.zeros((16, 16), complex)
+    for l in range(16):
+        src = (16 - l) & 15
+        for r in range(8):
+            V[l, r] = L[l, r]
+        for k2 in range(8, 16):
+            got = Mi[src, 15 - k2]
+            own = L[l, 8] if k2 == 8 else Mi[l, (16 - k2) & 7]
+            V[l, k2] = own if l == 0 else got
+    return V
+
+
+def check_lane_algebra(rng):
+    for inv in (False, True):
+        x = rng.standard_normal(16) + 1j * rng.standard_normal(16)
+        assert np.allclose(fft16_radix4(x, inv), np.fft.ifft(x) * 16 if inv else np.fft.fft(x))
+    a = rng.standard_normal(256); b = rng.standard_normal(256)
+    V = fft256_16x16(0.5 * (a + 1j * b))              # the 1/2 lives in the window
+    A, B = lanes_split_pair(V)
+    Fa, Fb = np.fft.rfft(a), np.fft.rfft(b)
+    for l in range(16):
+        for r in range(9 if l == 0 else 8):
+            assert np.allclose(A[l, r], Fa[l + 16 * r]) and np.allclose(B[l, r], Fb[l + 16 * r])
+    # inverse: P, Q half spectra (masked) -> frames p (re), q (im)
+    m1 = rng.random(129); m2 = rng.random(129)
+    P, Q = m1 * Fa, m2 * Fb
+    L = np.zeros((16, 9), complex); Mi = np.zeros((16, 9), complex)
+    for l in range(16):
+        for r in range(9):
+            k = l + 16 * r
+            if k <= 128:
+                L[l, r] = P[k] + 1j * Q[k]
+                Mi[l, r] = np.conj(P[k]) + 1j * np.conj(Q[k])
+    y = ifft256_16x16(lanes_merge_pair(L, Mi)) / 256
+    assert np.allclose(y.real, np.fft.irfft(P)) and np.allclose(y.imag, np.fft.irfft(Q))
+
+
 def main():
     rng = np.random.default_rng(0)
     for M in (16, 32, 64, 128, 256, 512, 1024):
@@ -125,6 +202,7 @@ def main():
     full = lambda H: np.concatenate([H, np.conj(H[-2:0:-1])])
     z = np.fft.ifft(full(Y1) + 1j * full(Y2))
     assert np.allclose(z.real, a) and np.allclose(z.imag, b)
+    check_lane_algebra(rng)
     print("fft emulation OK")
 
 
