@@ -206,14 +206,37 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double *red) {
     for (int i = 0; i < NV; ++i) red[warp * NV + i] = v[i];
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
+  // warp 0: lane i adds value i over the warps, in warp order (deterministic)
+  if (warp == 0) {
+    for (int i = lane; i < NV; i += 32) {
       double s = 0.0;
       for (int w = 0; w < nwarp; ++w) s += red[w * NV + i];
-      v[i] = s;
+      red[i] = s;     // safe: only lane i reads column i, and row 0 is read first
     }
   }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = red[i];
+  }
+}
+
+// ---- async copy helpers (sm_80+ LDGSTS, sm_90+ bulk prefetch) ----
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+// Pulls [ptr, ptr + bytes) towards L2 without occupying registers or shared
+// memory; ptr must be 16-byte aligned and bytes a multiple of 16.
+__device__ __forceinline__ void prefetch_l2_bulk(const void *ptr, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
 }
 
 // Lexicographic permutation p of n (n <= 4) into out[0..n).

@@ -315,6 +315,8 @@ extern "C" int sep_fused_separate_ws_f32(const sep_plan *p, const float *mix, co
   if ((rc = stage_out(s, scores, static_cast<size_t>(batch) * stride, mem, &d_scores))) return rc;
   if ((rc = stage_out(s, sums, static_cast<size_t>(4), mem, &d_sums))) return rc;
   a.n = n_samples;
+  a.batch = batch;
+  a.lookahead = 0;
   a.T = T;
   a.size = p->size;
   a.shift = p->shift;

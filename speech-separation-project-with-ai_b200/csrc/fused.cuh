@@ -16,6 +16,7 @@ struct FusedArgs {
   double *partials;       // [B * tiles, NV] or null (no refs)
   int64_t n;
   int T, size, shift, pad, tb, tiles;
+  int batch, lookahead;   // lookahead: tiles ahead of this CTA to pull into L2 (0 = off)
   const float *win_half, *syn;
   const float2 *tw_half, *tw_full, *tw16;
 };

@@ -35,7 +35,8 @@ struct FastGeom {
   static constexpr size_t smem(bool score) {
     return sizeof(float) * TILE * ((score ? 1 + C : 1) + C)   // wave tiles + accumulators
          + sizeof(float2) * kXchFloat2 * kUnits               // transpose buffers (also reduction scratch)
-         + sizeof(float) * 2 * N;                             // analysis / synthesis windows
+         + sizeof(float) * 2 * N                              // analysis / synthesis windows
+         + sizeof(float2) * 256;                              // W256^(p k) table, [k][p]
   }
 };
 
@@ -49,6 +50,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedAr
   float2 *xch_all = reinterpret_cast<float2 *>(acc + TILE * C);    // [kUnits][kXchFloat2]
   float *win = reinterpret_cast<float *>(xch_all + kXchFloat2 * kUnits);   // [N] 0.5 * analysis
   float *syn = win + N;                                            // [N] synthesis
+  float2 *twt = reinterpret_cast<float2 *>(syn + N);               // [16][16] twiddles, [j][lane]
 
   const int T = a.T, b = blockIdx.y, tile = blockIdx.x;
   const int own_lo = tile * TB, own_hi = min(own_lo + TB, T);
@@ -58,7 +60,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedAr
   const int unit = threadIdx.x >> 4, l16 = threadIdx.x & 15;
   float2 *xch = xch_all + unit * kXchFloat2;
 
-  // ---- stage waveforms (zeros outside [0, n)), clear accumulators, windows ----
+  // ---- stage waveforms asynchronously (zeros outside [0, n)), clear accumulators ----
   constexpr int NSIG = SCORE ? 1 + C : 1;
 #pragma unroll
   for (int sgn = 0; sgn < NSIG; ++sgn) {
@@ -67,41 +69,51 @@ __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedAr
     float *dst = tiles + TILE * sgn;
     const bool vec = ((reinterpret_cast<uintptr_t>(row + s0) & 15) == 0) && s0 >= 0 && s0 + TILE <= a.n;
     if (vec) {
-      for (int i = threadIdx.x; i < TILE / 4; i += kFastThreads)
-        reinterpret_cast<float4 *>(dst)[i] = __ldg(reinterpret_cast<const float4 *>(row + s0) + i);
+      for (int i = threadIdx.x; i < TILE / 4; i += kFastThreads) cp_async16(dst + 4 * i, row + s0 + 4 * i);
     } else {
       for (int i = threadIdx.x; i < TILE; i += kFastThreads) {
         const int64_t g = s0 + i;
-        dst[i] = (g >= 0 && g < a.n) ? __ldg(row + g) : 0.f;
+        if (g >= 0 && g < a.n) cp_async4(dst + i, row + g); else dst[i] = 0.f;
+      }
+    }
+  }
+  // pull the tile that a CTA of the next wave will stage into L2 (no registers, no smem)
+  if (a.lookahead > 0 && threadIdx.x == 0) {
+    const int64_t next = static_cast<int64_t>(b) * a.tiles + tile + a.lookahead;
+    const int nb = static_cast<int>(next / a.tiles), nt = static_cast<int>(next - static_cast<int64_t>(nb) * a.tiles);
+    if (nb < a.batch) {
+      const int n_lo = max(nt * TB - (R - 1), 0), n_hi = min(nt * TB + TB, T);
+      const int64_t w0 = max(static_cast<int64_t>(n_lo) * SHIFT - a.pad, static_cast<int64_t>(0));
+      const int64_t w1 = min(static_cast<int64_t>(n_lo) * SHIFT - a.pad + TILE, a.n);
+#pragma unroll
+      for (int sgn = 0; sgn < NSIG; ++sgn) {
+        const float *row = sgn == 0 ? a.mix + static_cast<int64_t>(nb) * a.n
+                                    : a.refs + (static_cast<int64_t>(nb) * C + (sgn - 1)) * a.n;
+        const uintptr_t p0 = (reinterpret_cast<uintptr_t>(row + w0) + 15) & ~uintptr_t(15);
+        const uintptr_t p1 = reinterpret_cast<uintptr_t>(row + w1) & ~uintptr_t(15);
+        if (p1 > p0) prefetch_l2_bulk(reinterpret_cast<const void *>(p0), static_cast<unsigned>(p1 - p0));
+      }
+#pragma unroll
+      for (int q = 0; q < C; ++q) {
+        const float *base = a.masks + (static_cast<int64_t>(nb) * C + q) * T * 129;
+        const uintptr_t p0 = (reinterpret_cast<uintptr_t>(base + static_cast<int64_t>(n_lo) * 129) + 15) & ~uintptr_t(15);
+        const uintptr_t p1 = reinterpret_cast<uintptr_t>(base + static_cast<int64_t>(n_hi) * 129) & ~uintptr_t(15);
+        if (p1 > p0) prefetch_l2_bulk(reinterpret_cast<const void *>(p0), static_cast<unsigned>(p1 - p0));
       }
     }
   }
   for (int i = threadIdx.x; i < TILE * C / 4; i += kFastThreads)
     reinterpret_cast<float4 *>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int i = threadIdx.x; i < N; i += kFastThreads) {
-    win[i] = __ldg(a.win_half + i);
-    syn[i] = __ldg(a.syn + i);
+  // constant tables ride the same async group (tw16 is symmetric: [j][p] == [p][j])
+  if (threadIdx.x < N / 4) {
+    cp_async16(win + 4 * threadIdx.x, a.win_half + 4 * threadIdx.x);
+    cp_async16(syn + 4 * threadIdx.x, a.syn + 4 * threadIdx.x);
   }
-  float2 tw[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) tw[j] = __ldg(a.tw16 + l16 * 16 + j);
-  __syncthreads();
+  cp_async16(twt + 2 * threadIdx.x, a.tw16 + 2 * threadIdx.x);
 
-  // ---- this half-warp's frame pair ----
+  // ---- this half-warp's frame pair; its mask rows are requested before the wait ----
   const int f0 = 2 * unit, f1 = f0 + 1;                // local frame indices
   const int ta = t_lo + f0, tb = t_lo + f1;            // global frame indices
-  float2 v[16];
-  float wl[16];
-#pragma unroll
-  for (int m = 0; m < 16; ++m) wl[m] = win[l16 + 16 * m];
-#pragma unroll
-  for (int m = 0; m < 16; ++m)
-    v[m] = make_float2(tiles[f0 * SHIFT + l16 + 16 * m] * wl[m], tiles[f1 * SHIFT + l16 + 16 * m] * wl[m]);
-  fft256<false>(v, tw, xch, l16);
-  float2 Xa[9], Xb[9];
-  split_pair(v, l16, Xa, Xb);
-
-  // masks of both frames at this lane's bins (coalesced 64-byte runs per row)
   float ma[C][9], mb[C][9];
 #pragma unroll
   for (int q = 0; q < C; ++q) {
@@ -113,6 +125,19 @@ __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedAr
       mb[q][r] = (bin_ok && tb < T) ? __ldg(base + static_cast<int64_t>(tb) * 129 + l16 + 16 * r) : 0.f;
     }
   }
+  const float2 *tw = twt + l16;
+  cp_async_wait_all();
+  __syncthreads();
+
+  float2 v[16];
+#pragma unroll
+  for (int m = 0; m < 16; ++m) {
+    const float w = win[l16 + 16 * m];
+    v[m] = make_float2(tiles[f0 * SHIFT + l16 + 16 * m] * w, tiles[f1 * SHIFT + l16 + 16 * m] * w);
+  }
+  fft256<false>(v, tw, xch, l16);
+  float2 Xa[9], Xb[9];
+  split_pair(v, l16, Xa, Xb);
 
   float pit[C * C];
 #pragma unroll
@@ -138,8 +163,10 @@ __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedAr
     for (int j = 0; j < C; ++j) {
       const float *ref = tiles + TILE * (1 + j);
 #pragma unroll
-      for (int m = 0; m < 16; ++m)
-        v[m] = make_float2(ref[f0 * SHIFT + l16 + 16 * m] * wl[m], ref[f1 * SHIFT + l16 + 16 * m] * wl[m]);
+      for (int m = 0; m < 16; ++m) {
+        const float w = win[l16 + 16 * m];
+        v[m] = make_float2(ref[f0 * SHIFT + l16 + 16 * m] * w, ref[f1 * SHIFT + l16 + 16 * m] * w);
+      }
       fft256<false>(v, tw, xch, l16);
       float2 Sa[9], Sb[9];
       split_pair(v, l16, Sa, Sb);
@@ -161,9 +188,6 @@ __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedAr
   }
 
   // ---- masked spectra -> time frames -> phased overlap-add ----
-  float sl[16];
-#pragma unroll
-  for (int m = 0; m < 16; ++m) sl[m] = syn[l16 + 16 * m];
 #pragma unroll
   for (int q = 0; q < C; ++q) {
     float2 L[9], Mi[9];
@@ -182,11 +206,11 @@ __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedAr
     for (int ph = 0; ph < R; ++ph) {
       if ((f0 % R) == ph) {
 #pragma unroll
-        for (int m = 0; m < 16; ++m) accq[f0 * SHIFT + l16 + 16 * m] += v[m].x * sl[m];
+        for (int m = 0; m < 16; ++m) accq[f0 * SHIFT + l16 + 16 * m] += v[m].x * syn[l16 + 16 * m];
       }
       if ((f1 % R) == ph) {
 #pragma unroll
-        for (int m = 0; m < 16; ++m) accq[f1 * SHIFT + l16 + 16 * m] += v[m].y * sl[m];
+        for (int m = 0; m < 16; ++m) accq[f1 * SHIFT + l16 + 16 * m] += v[m].y * syn[l16 + 16 * m];
       }
       __syncthreads();
     }
@@ -251,6 +275,7 @@ static int launch_fast(FusedArgs a, int batch, double *d_scores, double *d_sums,
   double *partials = nullptr;
   if (SCORE && (rc = s.alloc(&partials, static_cast<size_t>(batch) * a.tiles * G::NV))) return rc;
   a.partials = partials;
+  a.lookahead = 148 * 3;   // one wave of resident CTAs (3 per SM)
   const size_t smem = G::smem(SCORE);
   SEP_CUDA(cudaFuncSetAttribute(fused256_kernel<C, R, SCORE>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
