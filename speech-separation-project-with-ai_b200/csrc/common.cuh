@@ -108,7 +108,7 @@ struct Scratch {
     cudaError_t e = cudaMallocAsync(&p, bytes, stream);
     if (e != cudaSuccess) {
       set_error("cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
-      return SEP_ERR_NOMEM;
+      return e == cudaErrorMemoryAllocation ? SEP_ERR_NOMEM : SEP_ERR_CUDA;
     }
     blocks.push_back(p);
     *out = static_cast<T *>(p);
