@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--shift", type=int, default=128)
     ap.add_argument("--window", default="blackman", choices=["blackman", "hann", "hamming"])
+    ap.add_argument("--streams", type=int, default=3,
+                    help="independent steps captured round-robin on this many streams inside the graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -244,9 +246,9 @@ def run_sepcore(args):
     # ---- device-resident throughput: CUDA-graph replay, K steps exactly ----
     block = min(args.steps, 1024)
     n_blocks, tail = divmod(args.steps, block)
-    graph = sepcore.GraphedSeparator(dev_sets, block, **kw)
-    tail_graph = sepcore.GraphedSeparator(dev_sets, tail, **kw) if tail else None
-    warm = sepcore.GraphedSeparator(dev_sets, max(args.warmup, 3), **kw)
+    graph = sepcore.GraphedSeparator(dev_sets, block, streams=args.streams, **kw)
+    tail_graph = sepcore.GraphedSeparator(dev_sets, tail, streams=args.streams, **kw) if tail else None
+    warm = sepcore.GraphedSeparator(dev_sets, max(args.warmup, 3), streams=args.streams, **kw)
     warm.replay()
     if world > 1:
         dist.all_reduce(warm.sums)           # warms NCCL up too
@@ -276,7 +278,7 @@ def run_sepcore(args):
 
     # ---- roofline leg: the dominant kernel alone, bracketed by events in the library ----
     prof_steps = min(args.steps, 200)
-    ws = torch.empty(sepcore.workspace_bytes(args.batch, args.sources, n, args.size, args.shift, win),
+    ws = torch.zeros(sepcore.workspace_bytes(args.batch, args.sources, n, args.size, args.shift, win),
                      dtype=torch.uint8, device=dev)
     outs = {"est": torch.empty((args.batch, args.sources, n), device=dev),
             "scores": torch.empty((args.batch, sepcore.score_layout(args.sources)["stride"]),
@@ -358,13 +360,19 @@ def run_sepcore(args):
                        "samples_per_utt": n, "frames": frames, "bins": bins, "sources": args.sources,
                        "l2": "rotating %d distinct buffer sets (%.0f MB > 126 MB L2)"
                              % (N_SETS, N_SETS * bytes_per_launch / 1e6),
-                       "launch": "CUDA graph replay (%d-step graphs)" % block,
+                       "launch": "CUDA graph replay (%d-step graphs, independent steps round-robin on %d "
+                                 "streams inside the graph)" % (block, graph.n_streams),
                        "parallelism": "utterance-sharded x%d, all-reduce of per-batch sums bucketed per replay"
                                       % world},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "fused256_kernel (timed alone, one launch at a time, CUDA events "
+                                   "around the launch on its stream)",
                          "kernel_ms": kernel_ms_avg, "bytes_per_launch": bytes_per_launch,
-                         "launches_timed": bracketed},
+                         "launches_timed": bracketed,
+                         # the same bytes over the overlapped step time of the graph-replayed loop
+                         "achieved_in_loop": bytes_per_launch / (ms_total / args.steps * 1e-3) / 1e9,
+                         "frac_in_loop": bytes_per_launch / (ms_total / args.steps * 1e-3) / 1e9 / peak},
             "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps * world),
             "clocks": clocks, "check": {"pit_loss_sum": sums[0], "si_sdr_sum": sums[1], "n": sums[3]},
         }

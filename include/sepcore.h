@@ -162,7 +162,11 @@ int sep_fused_separate_f32(const sep_plan *plan, const float *mix, const float *
 /* As sep_fused_separate_f32, with caller-provided device scratch so that no
  * allocation happens inside the call (CUDA-graph capture, steady-state
  * serving).  workspace must hold sep_fused_workspace_bytes() bytes of device
- * memory; only meaningful with SEP_MEM_DEVICE (host mode ignores it). */
+ * memory and must be ZERO-FILLED before its first use (it carries the
+ * completion counters of the in-kernel finalisation; every successful call
+ * leaves them at zero, so one memset at allocation time is enough).  Do not
+ * share one workspace between calls that may run concurrently.  Only
+ * meaningful with SEP_MEM_DEVICE (host mode ignores it). */
 int sep_fused_workspace_bytes(const sep_plan *plan, int batch, int n_src, int64_t n_samples,
                               int64_t *bytes);
 int sep_fused_separate_ws_f32(const sep_plan *plan, const float *mix, const float *masks,

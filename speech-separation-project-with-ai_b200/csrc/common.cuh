@@ -177,14 +177,29 @@ inline int factorial(int n) {
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__
 
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+// Complex arithmetic on Blackwell's packed FP32 pipe: sm_100 FADD2 / FMUL2 / FFMA2
+// work on (lo, hi) register pairs with per-operand half swizzles and per-half
+// negation, so a complex add, an add with a +-i rotation or a conjugate costs ONE
+// instruction and a complex multiply TWO (nvcc folds the make_float2 shuffles
+// below into operand modifiers: FADD2 R, a.HI_LO, b.LO_HI.NP).
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 cadd_mi(float2 a, float2 b) {   // a - i b
+  return __fadd2_rn(a, make_float2(b.y, -b.x));
+}
+__device__ __forceinline__ float2 cadd_pi(float2 a, float2 b) {   // a + i b
+  return __fadd2_rn(a, make_float2(-b.y, b.x));
+}
+__device__ __forceinline__ float2 cadd_conj(float2 a, float2 b) {  // a + conj(b)
+  return __fadd2_rn(a, make_float2(b.x, -b.y));
+}
+__device__ __forceinline__ float2 cscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {      // a * b
+  return __ffma2_rn(make_float2(-a.y, a.x), make_float2(b.y, b.y), __fmul2_rn(a, make_float2(b.x, b.x)));
 }
 __device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {  // a * conj(b)
-  return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+  return __ffma2_rn(make_float2(a.y, -a.x), make_float2(b.y, b.y), __fmul2_rn(a, make_float2(b.x, b.x)));
 }
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

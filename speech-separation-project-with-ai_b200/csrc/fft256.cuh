@@ -24,12 +24,11 @@ constexpr int kXchFloat2 = 16 * kXchPitch;       // per half-warp
 template <bool INV>
 __device__ __forceinline__ void fft4(float2 &x0, float2 &x1, float2 &x2, float2 &x3) {
   const float2 t0 = cadd(x0, x2), t1 = csub(x0, x2), t2 = cadd(x1, x3), t3 = csub(x1, x3);
-  // forward: X1 = t1 - i t3, X3 = t1 + i t3 ; inverse: swapped
-  const float2 r = INV ? make_float2(-t3.y, t3.x) : make_float2(t3.y, -t3.x);
+  // forward: X1 = t1 - i t3, X3 = t1 + i t3 ; inverse: swapped.  8 packed adds in all.
   x0 = cadd(t0, t2);
   x2 = csub(t0, t2);
-  x1 = cadd(t1, r);
-  x3 = csub(t1, r);
+  x1 = INV ? cadd_pi(t1, t3) : cadd_mi(t1, t3);
+  x3 = INV ? cadd_mi(t1, t3) : cadd_pi(t1, t3);
 }
 
 // v *= W16^e (forward) or its conjugate (inverse), e in {1, 2, 3, 4, 6, 9}
@@ -40,8 +39,8 @@ __device__ __forceinline__ float2 tw16(float2 v) {
   constexpr float wr = (E == 1) ? c1 : (E == 2) ? r : (E == 3) ? s1 : (E == 4) ? 0.f : (E == 6) ? -r : -c1;
   constexpr float wi0 = (E == 1) ? -s1 : (E == 2) ? -r : (E == 3) ? -c1 : (E == 4) ? -1.f : (E == 6) ? -r : s1;
   constexpr float wi = INV ? -wi0 : wi0;
-  if (E == 4) return make_float2(-v.y * wi, v.x * wi);      // +-i * v, wi = -+1
-  return make_float2(fmaf(v.x, wr, -v.y * wi), fmaf(v.x, wi, v.y * wr));
+  if (E == 4) return INV ? cadd_pi(make_float2(0.f, 0.f), v) : cadd_mi(make_float2(0.f, 0.f), v);
+  return cmul(v, make_float2(wr, wi));
 }
 
 // In-register 16-point FFT, natural order in and out (n = 4a + b, k = c + 4d).
@@ -107,8 +106,9 @@ __device__ __forceinline__ void split_pair(const float2 (&v)[16], int l16, float
     const float2 own = v[(16 - r) & 15];
     const float2 zp = (l16 == 0) ? own : got;
     const float2 z = v[r];
-    A[r] = make_float2(z.x + zp.x, z.y - zp.y);
-    B[r] = make_float2(z.y + zp.y, zp.x - z.x);
+    A[r] = cadd_conj(z, zp);                                   // Z + conj Z'
+    const float2 d = __fadd2_rn(z, make_float2(-zp.x, zp.y));  // Z - conj Z'
+    B[r] = make_float2(d.y, -d.x);                             // -i (Z - conj Z')
   }
 }
 

@@ -264,7 +264,7 @@ extern "C" int sep_fused_workspace_bytes(const sep_plan *p, int batch, int n_src
   sep_plan_frames(p, n_samples, &T);
   // worst case: one tile per frame, NV doubles per tile, plus alignment slack
   const int64_t nv = 2 * n_src * n_src + 2 * n_src;
-  *bytes = static_cast<int64_t>(batch) * T * nv * 8 + 4096;
+  *bytes = static_cast<int64_t>(batch) * T * nv * 8 + (static_cast<int64_t>(batch) + 1) * 4 + 4096;
   return SEP_OK;
 }
 

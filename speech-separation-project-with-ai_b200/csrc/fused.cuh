@@ -14,6 +14,9 @@ struct FusedArgs {
   const int32_t *valid;   // [B] or null
   float *est;             // [B, C, n] or null
   double *partials;       // [B * tiles, NV] or null (no refs)
+  double *scores;         // [B, stride]   (in-kernel finalisation, fast path)
+  double *sums;           // [4] or null
+  int *counters;          // [B + 1] zero on entry, left zero: tiles done per utterance, utterances done
   int64_t n;
   int T, size, shift, pad, tb, tiles;
   int batch, lookahead;   // lookahead: tiles ahead of this CTA to pull into L2 (0 = off)
@@ -52,6 +55,63 @@ __global__ void fused_finalize_kernel(const double *__restrict__ partials, int t
     finalize_pit<C>(v, len, row);
     finalize_scores<C>(v + C * C, v + 2 * C * C, v + 2 * C * C + C, row + C * C + P + 2);
   }
+}
+
+// Last-tile-done finalisation inside the producing kernel (one launch per step).
+// Called by every thread of a CTA after its partial row has been written by thread 0.
+// The CTA that completes an utterance reduces that utterance's partials in tile order
+// (same arithmetic as fused_finalize_kernel, so results are bit-identical); the CTA
+// that completes the last utterance adds the batch sums in utterance order.  The
+// counters are left at zero for the next launch.
+template <int C>
+__device__ __forceinline__ void finalize_in_kernel(const FusedArgs &a, int b, int *s_flag) {
+  constexpr int NV = FusedVals<C>::NV;
+  constexpr int P = (C == 1) ? 1 : (C == 2) ? 2 : (C == 3) ? 6 : 24;
+  constexpr int STRIDE = 3 * C * C + P + 6;
+  if (threadIdx.x == 0) {
+    __threadfence();                                        // publish this tile's partials
+    *s_flag = atomicAdd(a.counters + b, 1) == a.tiles - 1;
+  }
+  __syncthreads();
+  if (!*s_flag || threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  __threadfence();
+  double v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = 0.0;
+  for (int t = lane; t < a.tiles; t += 32) {
+    const double *src = a.partials + (static_cast<int64_t>(b) * a.tiles + t) * NV;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] += __ldcg(src + i);
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  int last_utt = 0;
+  if (lane == 0) {
+    double *row = a.scores + static_cast<int64_t>(b) * STRIDE;
+    const double len = a.lengths ? static_cast<double>(a.lengths[b]) : static_cast<double>(a.T);
+    finalize_pit<C>(v, len, row);
+    finalize_scores<C>(v + C * C, v + 2 * C * C, v + 2 * C * C + C, row + C * C + P + 2);
+    a.counters[b] = 0;
+    __threadfence();                                        // publish the score row
+    last_utt = atomicAdd(a.counters + a.batch, 1) == a.batch - 1;
+  }
+  last_utt = __shfl_sync(0xffffffffu, last_utt, 0);
+  if (!last_utt) return;
+  __threadfence();
+  if (a.sums) {
+    constexpr int off_pit = C * C + P + 1, off_si = C * C + P + 2 + C * C, off_sdr = off_si + 2 + C * C;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int u = lane; u < a.batch; u += 32) {
+      const double *row = a.scores + static_cast<int64_t>(u) * STRIDE;
+      s0 += __ldcg(row + off_pit);
+      s1 += __ldcg(row + off_si);
+      s2 += __ldcg(row + off_sdr);
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0) { a.sums[0] = s0; a.sums[1] = s1; a.sums[2] = s2; a.sums[3] = a.batch; }
+  }
+  if (lane == 0) a.counters[a.batch] = 0;
 }
 
 // sums[4] = {sum pit_loss, sum si_best, sum sdr_best, batch}; one warp, fixed order.

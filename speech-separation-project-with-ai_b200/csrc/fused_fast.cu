@@ -132,8 +132,8 @@ __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedAr
   float2 v[16];
 #pragma unroll
   for (int m = 0; m < 16; ++m) {
-    const float w = win[l16 + 16 * m];
-    v[m] = make_float2(tiles[f0 * SHIFT + l16 + 16 * m] * w, tiles[f1 * SHIFT + l16 + 16 * m] * w);
+    v[m] = cscale(make_float2(tiles[f0 * SHIFT + l16 + 16 * m], tiles[f1 * SHIFT + l16 + 16 * m]),
+                  win[l16 + 16 * m]);
   }
   fft256<false>(v, tw, xch, l16);
   float2 Xa[9], Xb[9];
@@ -164,8 +164,8 @@ __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedAr
       const float *ref = tiles + TILE * (1 + j);
 #pragma unroll
       for (int m = 0; m < 16; ++m) {
-        const float w = win[l16 + 16 * m];
-        v[m] = make_float2(ref[f0 * SHIFT + l16 + 16 * m] * w, ref[f1 * SHIFT + l16 + 16 * m] * w);
+        v[m] = cscale(make_float2(ref[f0 * SHIFT + l16 + 16 * m], ref[f1 * SHIFT + l16 + 16 * m]),
+                      win[l16 + 16 * m]);
       }
       fft256<false>(v, tw, xch, l16);
       float2 Sa[9], Sb[9];
@@ -194,10 +194,9 @@ __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedAr
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
       // P = m_a X_a (frame ta, real part), Q = m_b X_b (frame tb, imaginary part)
-      const float2 P = make_float2(ma[q][r] * Xa[r].x, ma[q][r] * Xa[r].y);
-      const float2 Q = make_float2(mb[q][r] * Xb[r].x, mb[q][r] * Xb[r].y);
-      L[r] = make_float2(P.x - Q.y, P.y + Q.x);       // P + i Q
-      Mi[r] = make_float2(P.x + Q.y, Q.x - P.y);      // conj P + i conj Q
+      const float2 P = cscale(Xa[r], ma[q][r]), Q = cscale(Xb[r], mb[q][r]);
+      L[r] = cadd_pi(P, Q);                                          // P + i Q
+      Mi[r] = __fadd2_rn(make_float2(P.x, -P.y), make_float2(Q.y, Q.x));   // conj P + i conj Q
     }
     merge_pair(v, l16, L, Mi);
     fft256<true>(v, tw, xch, l16);
@@ -263,6 +262,10 @@ __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedAr
 #pragma unroll
     for (int i = 0; i < NV; ++i) dst[i] = vals[i];
   }
+  if (a.counters != nullptr) {      // single-launch mode: last tile of an utterance finalises it
+    __shared__ int s_flag;
+    finalize_in_kernel<C>(a, b, &s_flag);
+  }
 }
 
 template <int C, int R, bool SCORE>
@@ -273,8 +276,20 @@ static int launch_fast(FusedArgs a, int batch, double *d_scores, double *d_sums,
   a.tiles = (a.T + G::TB - 1) / G::TB;
   int rc;
   double *partials = nullptr;
-  if (SCORE && (rc = s.alloc(&partials, static_cast<size_t>(batch) * a.tiles * G::NV))) return rc;
+  int *counters = nullptr;
+  static const bool single_launch = getenv("SEPCORE_SINGLE_LAUNCH") != nullptr;
+  if (SCORE) {
+    // counters first: with a caller workspace they sit at its start, which the caller
+    // zero-filled once and every launch leaves at zero
+    if ((rc = s.alloc(&counters, static_cast<size_t>(batch) + 1))) return rc;
+    if ((rc = s.alloc(&partials, static_cast<size_t>(batch) * a.tiles * G::NV))) return rc;
+    if (!single_launch) counters = nullptr;
+    else if (!s.arena) SEP_CUDA(cudaMemsetAsync(counters, 0, sizeof(int) * (batch + 1), stream));
+  }
   a.partials = partials;
+  a.counters = counters;
+  a.scores = d_scores;
+  a.sums = d_sums;
   a.lookahead = 148 * 3;   // one wave of resident CTAs (3 per SM)
   const size_t smem = G::smem(SCORE);
   SEP_CUDA(cudaFuncSetAttribute(fused256_kernel<C, R, SCORE>,
@@ -284,7 +299,7 @@ static int launch_fast(FusedArgs a, int batch, double *d_scores, double *d_sums,
   fused256_kernel<C, R, SCORE><<<grid, kFastThreads, smem, stream>>>(a);
   profile_end(stream);
   SEP_LAUNCHED();
-  if (SCORE) return launch_fused_finalize<C>(a, batch, d_scores, d_sums, stream);
+  if (SCORE && counters == nullptr) return launch_fused_finalize<C>(a, batch, d_scores, d_sums, stream);
   return SEP_OK;
 }
 

@@ -67,8 +67,10 @@ def separate_and_score(mix, masks, refs=None, frame_lengths=None, valid_samples=
     numpy in -> numpy out (library stages copies); CUDA tensors in -> CUDA tensors out.
     `out` may carry preallocated 'est' / 'scores' / 'sums' buffers (CUDA tensors in
     device mode; numpy arrays -- e.g. views of pinned memory -- in host mode).
-    `workspace` (device mode): a uint8 CUDA tensor of `workspace_bytes(...)` bytes;
-    with it the call allocates nothing, so it can be captured into a CUDA graph.
+    `workspace` (device mode): a ZERO-FILLED uint8 CUDA tensor of `workspace_bytes(...)`
+    bytes (`torch.zeros`; the library leaves it zero-filled, so one buffer can be
+    reused by successive calls on one stream); with it the call allocates nothing, so
+    it can be captured into a CUDA graph.
     """
     plan = get_plan(size, shift, window, True)
     lib = _lib.load()

@@ -18,9 +18,14 @@ class GraphedSeparator:
     optional 'refs' [B,C,N], 'frame_lengths', 'valid_samples'.  Each set gets its
     own output buffers ('est', 'scores', 'sums') -- replaying never allocates.
     steps: how many fused steps one replay runs; step s uses set s % len(sets).
+    streams: independent steps are captured round-robin on this many streams (fork /
+    join inside the graph), so the serial tail of one step (last tile -> utterance
+    finalisation -> batch sums) and its last partial wave of CTAs overlap the next
+    step's main phase.  Needs streams <= len(buffer_sets): concurrent steps never
+    share buffers or workspaces.
     """
 
-    def __init__(self, buffer_sets, steps, size=256, shift=128, window=None, want_est=True):
+    def __init__(self, buffer_sets, steps, size=256, shift=128, window=None, want_est=True, streams=1):
         import torch
 
         self.sets = buffer_sets
@@ -37,7 +42,7 @@ class GraphedSeparator:
         self.sums = torch.zeros((self.steps, 4), dtype=torch.float64, device=dev) if scored else None
         self.outs = []
         for _ in buffer_sets:
-            o = {"workspace": torch.empty(nbytes, dtype=torch.uint8, device=dev)}
+            o = {"workspace": torch.zeros(nbytes, dtype=torch.uint8, device=dev)}   # zero-filled once
             if want_est:
                 o["est"] = torch.empty((batch, n_src, n), dtype=torch.float32, device=dev)
             if first.get("refs") is not None:
@@ -52,10 +57,22 @@ class GraphedSeparator:
                 self._step(i, 0)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        self.n_streams = max(1, min(int(streams), len(buffer_sets), max(self.steps, 1)))
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            for s in range(self.steps):
-                self._step(s % len(buffer_sets), s)
+            main = torch.cuda.current_stream(dev)
+            if self.n_streams == 1:
+                for s in range(self.steps):
+                    self._step(s % len(buffer_sets), s)
+            else:
+                lanes = [torch.cuda.Stream(device=dev) for _ in range(self.n_streams)]
+                for lane in lanes:                       # fork
+                    lane.wait_stream(main)
+                for s in range(self.steps):
+                    with torch.cuda.stream(lanes[s % self.n_streams]):
+                        self._step(s % len(buffer_sets), s)
+                for lane in lanes:                       # join
+                    main.wait_stream(lane)
 
     def _step(self, i, s):
         b, o = self.sets[i], dict(self.outs[i])
