@@ -319,28 +319,45 @@ def run_sepcore(args):
                    "sums": torch.empty(4, dtype=torch.float64).pin_memory()}
         np_out = {k: v.numpy() for k, v in pin_out.items()}
         np_in = [{k: v.numpy() for k, v in s.items()} for s in pin]
-        e2e_steps = max(3, min(args.steps, 50))
+        e2e_steps = max(3, min(args.steps, 100))
+        pipe = sepcore.HostPipeline(args.batch, args.sources, n, depth=3, **kw)
         for s in range(3):
-            sepcore.separate_and_score(np_in[s]["mix"], np_in[s]["masks"], np_in[s]["refs"], out=np_out, **kw)
+            pipe.submit(pin[s]["mix"], pin[s]["masks"], pin[s]["refs"])
+        pipe.drain()
         barrier()
         t0 = time.perf_counter()
+        loss, tickets = 0.0, []
         for s in range(e2e_steps):
-            d = np_in[s % N_SETS]
-            res = sepcore.separate_and_score(d["mix"], d["masks"], d["refs"], out=np_out, **kw)
-            _ = float(res["sums"][0])       # the step's loss, read on the host
+            d = pin[s % N_SETS]
+            tickets.append(pipe.submit(d["mix"], d["masks"], d["refs"]))   # H2D + kernels + D2H of step s
+            if s >= 2:
+                loss += float(pipe.result(tickets[s - 2])["sums"][0])       # step s-2's loss, read on the host
+        for t in tickets[max(e2e_steps - 2, 0):]:
+            loss += float(pipe.result(t)["sums"][0])
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-        h2d = sum(v.nbytes for v in np_in[0].values())
-        d2h = sum(v.nbytes for v in np_out.values())
+        # the synchronous drop-in call on the same buffers, for reference
+        sync_steps = max(3, min(args.steps, 30))
+        for s in range(3):
+            sepcore.separate_and_score(np_in[s]["mix"], np_in[s]["masks"], np_in[s]["refs"], out=np_out, **kw)
+        t0 = time.perf_counter()
+        for s in range(sync_steps):
+            d = np_in[s % N_SETS]
+            res = sepcore.separate_and_score(d["mix"], d["masks"], d["refs"], out=np_out, **kw)
+            _ = float(res["sums"][0])
+        dt_sync = (time.perf_counter() - t0) / sync_steps
         e2e = {"value": world * e2e_steps * args.batch * args.seconds / dt, "unit": UNIT,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-               "ms_per_step": 1e3 * dt / e2e_steps,
-               "api": "sepcore.separate_and_score(numpy views of pinned host memory) -> "
-                      "sep_fused_separate_ws_f32(SEP_MEM_HOST)"}
+               "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
+               "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
+               "api": "sepcore.HostPipeline.submit/result on pinned host buffers (3 slots; copy-in, "
+                      "compute, copy-out streams) -> sep_fused_separate_ws_f32",
+               "sync_call_ms_per_step": 1e3 * dt_sync,
+               "sync_call": "sepcore.separate_and_score(numpy views of pinned memory), SEP_MEM_HOST",
+               "loss_sum": loss}
     clocks = sampler.summary()
 
     cpu = None

@@ -17,6 +17,7 @@ from .scoring import (permute_si_sdr, pow_norm, pow_np_norm, score_batch, score_
 from .filterbank import conv1d, segment_raw
 from .fused import parse_scores, score_layout, separate_and_score, workspace_bytes
 from .graphs import GraphedSeparator
+from .pipeline import HostPipeline
 from . import distributed
 
 __all__ = [
@@ -26,6 +27,6 @@ __all__ = [
     "pit_mse", "pit_with_outputsize",
     "pow_np_norm", "pow_norm", "si_sdr", "permute_si_sdr", "score_batch", "score_flat_device",
     "truncate_to_min_len", "conv1d", "segment_raw",
-    "separate_and_score", "score_layout", "parse_scores", "workspace_bytes", "GraphedSeparator",
+    "separate_and_score", "score_layout", "parse_scores", "workspace_bytes", "GraphedSeparator", "HostPipeline",
     "distributed",
 ]

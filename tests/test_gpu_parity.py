@@ -405,3 +405,70 @@ def test_conv1d_variants(sep, oracle, stride, padding, taps, act):
     got = sep.conv1d(x, w, None, stride=stride, padding=padding, activation=act)
     want = oracle.conv1d(x, w, None, stride=stride, padding=padding, activation=act)
     assert got.shape == want.shape and np.max(np.abs(got - want)) < 2e-5
+
+
+# ----------------------------------------------------------------- launch plumbing
+def test_host_pipeline_and_graph_match_sync_call(sep, oracle):
+    """HostPipeline (3 streams, slots) and GraphedSeparator (multi-stream CUDA graph)
+    run the same C-ABI call: results must be bit-identical to the synchronous call."""
+    import torch
+    rng = np.random.default_rng(21)
+    cfg = CONFIGS["blackman_256_128"]
+    cases = [_fused_case(rng, 4, 8000, 2, cfg, oracle)[:3] for _ in range(5)]
+    want = [sep.separate_and_score(m, k, r, **cfg) for m, r, k in cases]
+    pipe = sep.HostPipeline(4, 2, 8000, depth=3, **cfg)
+    tickets = []
+    for i, (m, r, k) in enumerate(cases):
+        tickets.append(pipe.submit(m, k, r))
+        if i >= 2:
+            got = pipe.result(tickets[i - 2])
+            assert np.array_equal(got["est"], want[i - 2]["est"])
+            assert np.array_equal(got["scores"], want[i - 2]["scores"])
+    for i in (3, 4):
+        got = pipe.result(tickets[i])
+        assert np.array_equal(got["scores"], want[i]["scores"]) and np.array_equal(got["sums"], want[i]["sums"])
+    with pytest.raises(ValueError):
+        pipe.result(0)                                    # slot already reused
+    sets = [{"mix": torch.from_numpy(m).cuda(), "refs": torch.from_numpy(r).cuda(),
+             "masks": torch.from_numpy(k).cuda()} for m, r, k in cases[:3]]
+    for streams in (1, 3):
+        g = sep.GraphedSeparator(sets, steps=6, streams=streams, **cfg)
+        g.replay()
+        torch.cuda.synchronize()
+        for i in range(3):
+            res = g.results(i)
+            assert np.array_equal(res["est"].cpu().numpy(), want[i]["est"])
+            assert np.array_equal(res["pit_perm"].cpu().numpy(), want[i]["pit_perm"])
+            assert np.array_equal(g.sums[i].cpu().numpy(), want[i]["sums"])
+            assert np.array_equal(g.sums[i + 3].cpu().numpy(), want[i]["sums"])
+
+
+def test_single_launch_finalisation_matches(sep, oracle, monkeypatch):
+    """SEPCORE_SINGLE_LAUNCH=1 folds the finalisation into the fused kernel (last tile of an
+    utterance finalises it): same arithmetic, bit-identical scores.  Run in a subprocess
+    because the switch is read once per process."""
+    import subprocess, sys, os, textwrap
+    code = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path[:0] = [%r, %r]
+        import sepcore
+        rng = np.random.default_rng(5)
+        refs = (0.1 * rng.standard_normal((5, 2, 9000))).astype(np.float32)
+        mix = refs.sum(1).astype(np.float32)
+        T = sepcore.get_plan(256, 128).frames(9000)
+        masks = rng.random((5, 2, T, 129)).astype(np.float32)
+        res = sepcore.separate_and_score(mix, masks, refs, size=256, shift=128)
+        np.save(sys.argv[1], np.concatenate([res['scores'].ravel(), res['sums']]))
+    """) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+            os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                         "speech-separation-project-with-ai_b200"))
+    outs = []
+    for flag in ("", "1"):
+        env = dict(os.environ)
+        env.pop("SEPCORE_SINGLE_LAUNCH", None)
+        if flag:
+            env["SEPCORE_SINGLE_LAUNCH"] = flag
+        path = "/tmp/sepcore_single_%s.npy" % (flag or "0")
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env)
+        outs.append(np.load(path))
+    assert np.array_equal(outs[0], outs[1])
