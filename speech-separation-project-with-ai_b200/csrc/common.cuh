@@ -68,6 +68,10 @@ struct sep_plan {
   float2 *d_tw_half = nullptr;   // exp(-2 pi i k / half), k < half
   float2 *d_tw_full = nullptr;   // exp(-2 pi i k / size), k <= half
   float2 *d_tw16 = nullptr;      // exp(-2 pi i p*k / 256) [16][16] for the 16x16 FFT
+  // size 256 only: windows as [16 lanes][18] (lane p holds taps p + 16 m at [p*18 + m]; the
+  // pitch of 18 makes a half-warp's paired loads conflict-free)
+  float *d_win_t = nullptr;      // 0.5 * analysis
+  float *d_syn_t = nullptr;      // synthesis
 };
 
 namespace sep {

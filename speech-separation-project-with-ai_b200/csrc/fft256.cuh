@@ -68,9 +68,9 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = o[i];
 }
 
-// 256-point complex FFT on 16 lanes.  tw points at this lane's column of the
-// shared twiddle table: tw[16 * j] = exp(-2 pi i * l16 * j / 256) (lanes read
-// consecutive float2, conflict-free).
+// 256-point complex FFT on 16 lanes.  tw points at this lane's column of the shared
+// twiddle table: tw[16 * j] = exp(-2 pi i * l16 * j / 256) (lanes read consecutive
+// float2: conflict-free, and both half-warps read the same words: broadcast).
 // xch: this half-warp's private transpose buffer (kXchFloat2 float2).
 template <bool INV>
 __device__ __forceinline__ void fft256(float2 (&v)[16], const float2 *tw, float2 *xch, int l16) {

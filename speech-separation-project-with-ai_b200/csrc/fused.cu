@@ -326,6 +326,8 @@ extern "C" int sep_fused_separate_ws_f32(const sep_plan *p, const float *mix, co
   a.tw_half = p->d_tw_half;
   a.tw_full = p->d_tw_full;
   a.tw16 = p->d_tw16;
+  a.win_t = p->d_win_t;
+  a.syn_t = p->d_syn_t;
 
   bool handled = false;
   if ((rc = fused_fast_try(p, a, batch, C, d_scores, d_sums, s, stream, &handled))) return rc;

@@ -31,26 +31,33 @@ struct FastGeom {
   static constexpr int FRAMES = 2 * kUnits;            // frames transformed per tile
   static constexpr int TB = FRAMES - (R - 1);          // owned frames / output hop-blocks
   static constexpr int TILE = (FRAMES - 1) * SHIFT + N;   // staged samples == accumulator span
+  // Shared layout of a tile / accumulator: sample i lives at i + 16 * (i / (2 * SHIFT)).
+  // The two half-warps of a warp work on frames 2 * SHIFT samples apart (a multiple of
+  // 32 banks); the skew moves them 16 banks apart, so their 16-lane accesses never collide.
+  static constexpr int SKEW_SPAN = 2 * SHIFT;
+  static constexpr int TILE_SK = ((TILE - 1) + 16 * ((TILE - 1) / SKEW_SPAN) + 1 + 3) & ~3;
+  static constexpr int WT = 16 * 18 + 8;                  // transposed window table, floats
   static constexpr int NV = FusedVals<C>::NV;
   static constexpr size_t smem(bool score) {
-    return sizeof(float) * TILE * ((score ? 1 + C : 1) + C)   // wave tiles + accumulators
-         + sizeof(float2) * kXchFloat2 * kUnits               // transpose buffers (also reduction scratch)
-         + sizeof(float) * 2 * N                              // analysis / synthesis windows
-         + sizeof(float2) * 256;                              // W256^(p k) table, [k][p]
+    return sizeof(float) * TILE_SK * ((score ? 1 + C : 1) + C)   // wave tiles + accumulators
+         + sizeof(float2) * kXchFloat2 * kUnits                  // transpose buffers (also reduction scratch)
+         + sizeof(float) * 2 * WT                                // analysis / synthesis windows [16][18]
+         + sizeof(float2) * 256;                                 // W256^(p k) table, [k][p]
   }
+  __host__ __device__ static constexpr int sk(int i) { return i + 16 * (i / SKEW_SPAN); }
 };
 
 template <int C, int R, bool SCORE>
 __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedArgs a) {
   using G = FastGeom<C, R>;
-  constexpr int N = G::N, SHIFT = G::SHIFT, TILE = G::TILE, TB = G::TB;
+  constexpr int SHIFT = G::SHIFT, TILE = G::TILE, TSK = G::TILE_SK, TB = G::TB, SPAN = G::SKEW_SPAN;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float *tiles = reinterpret_cast<float *>(smem_raw);              // [1 (+C)][TILE]
-  float *acc = tiles + TILE * (SCORE ? 1 + C : 1);                 // [C][TILE]
-  float2 *xch_all = reinterpret_cast<float2 *>(acc + TILE * C);    // [kUnits][kXchFloat2]
-  float *win = reinterpret_cast<float *>(xch_all + kXchFloat2 * kUnits);   // [N] 0.5 * analysis
-  float *syn = win + N;                                            // [N] synthesis
-  float2 *twt = reinterpret_cast<float2 *>(syn + N);               // [16][16] twiddles, [j][lane]
+  float *tiles = reinterpret_cast<float *>(smem_raw);              // [1 (+C)][TSK], skewed
+  float *acc = tiles + TSK * (SCORE ? 1 + C : 1);                  // [C][TSK], skewed
+  float2 *xch_all = reinterpret_cast<float2 *>(acc + TSK * C);     // [kUnits][kXchFloat2]
+  float *win = reinterpret_cast<float *>(xch_all + kXchFloat2 * kUnits);   // [16][18] 0.5 * analysis
+  float *syn = win + G::WT;                                        // [16][18] synthesis
+  float2 *twt = reinterpret_cast<float2 *>(syn + G::WT);           // [16][16] twiddles, [j][lane]
 
   const int T = a.T, b = blockIdx.y, tile = blockIdx.x;
   const int own_lo = tile * TB, own_hi = min(own_lo + TB, T);
@@ -62,23 +69,25 @@ __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedAr
 
   // ---- stage waveforms asynchronously (zeros outside [0, n)), clear accumulators ----
   constexpr int NSIG = SCORE ? 1 + C : 1;
+  if (!(a.debug_skip & 32))
 #pragma unroll
   for (int sgn = 0; sgn < NSIG; ++sgn) {
     const float *row = sgn == 0 ? a.mix + static_cast<int64_t>(b) * a.n
                                 : a.refs + (static_cast<int64_t>(b) * C + (sgn - 1)) * a.n;
-    float *dst = tiles + TILE * sgn;
+    float *dst = tiles + TSK * sgn;
     const bool vec = ((reinterpret_cast<uintptr_t>(row + s0) & 15) == 0) && s0 >= 0 && s0 + TILE <= a.n;
     if (vec) {
-      for (int i = threadIdx.x; i < TILE / 4; i += kFastThreads) cp_async16(dst + 4 * i, row + s0 + 4 * i);
+      for (int i = threadIdx.x; i < TILE / 4; i += kFastThreads)
+        cp_async16(dst + G::sk(4 * i), row + s0 + 4 * i);
     } else {
       for (int i = threadIdx.x; i < TILE; i += kFastThreads) {
         const int64_t g = s0 + i;
-        if (g >= 0 && g < a.n) cp_async4(dst + i, row + g); else dst[i] = 0.f;
+        if (g >= 0 && g < a.n) cp_async4(dst + G::sk(i), row + g); else dst[G::sk(i)] = 0.f;
       }
     }
   }
   // pull the tile that a CTA of the next wave will stage into L2 (no registers, no smem)
-  if (a.lookahead > 0 && threadIdx.x == 0) {
+  if (a.lookahead > 0 && threadIdx.x == 0 && !(a.debug_skip & 64)) {
     const int64_t next = static_cast<int64_t>(b) * a.tiles + tile + a.lookahead;
     const int nb = static_cast<int>(next / a.tiles), nt = static_cast<int>(next - static_cast<int64_t>(nb) * a.tiles);
     if (nb < a.batch) {
@@ -102,14 +111,14 @@ __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedAr
       }
     }
   }
-  for (int i = threadIdx.x; i < TILE * C / 4; i += kFastThreads)
+  for (int i = threadIdx.x; i < TSK * C / 4; i += kFastThreads)
     reinterpret_cast<float4 *>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  // constant tables ride the same async group (tw16 is symmetric: [j][p] == [p][j])
-  if (threadIdx.x < N / 4) {
-    cp_async16(win + 4 * threadIdx.x, a.win_half + 4 * threadIdx.x);
-    cp_async16(syn + 4 * threadIdx.x, a.syn + 4 * threadIdx.x);
+  // the window tables ride the same async group
+  if (threadIdx.x < G::WT / 4) {
+    cp_async16(win + 4 * threadIdx.x, a.win_t + 4 * threadIdx.x);
+    cp_async16(syn + 4 * threadIdx.x, a.syn_t + 4 * threadIdx.x);
   }
-  cp_async16(twt + 2 * threadIdx.x, a.tw16 + 2 * threadIdx.x);
+  cp_async16(twt + 2 * threadIdx.x, a.tw16 + 2 * threadIdx.x);   // symmetric: [j][p] == [p][j]
 
   // ---- this half-warp's frame pair; its mask rows are requested before the wait ----
   const int f0 = 2 * unit, f1 = f0 + 1;                // local frame indices
@@ -121,28 +130,36 @@ __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedAr
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
       const bool bin_ok = r < 8 || l16 == 0;
-      ma[q][r] = (bin_ok && ta < T) ? __ldg(base + static_cast<int64_t>(ta) * 129 + l16 + 16 * r) : 0.f;
-      mb[q][r] = (bin_ok && tb < T) ? __ldg(base + static_cast<int64_t>(tb) * 129 + l16 + 16 * r) : 0.f;
+      ma[q][r] = (bin_ok && ta < T && !(a.debug_skip & 16)) ? __ldg(base + static_cast<int64_t>(ta) * 129 + l16 + 16 * r) : 0.f;
+      mb[q][r] = (bin_ok && tb < T && !(a.debug_skip & 16)) ? __ldg(base + static_cast<int64_t>(tb) * 129 + l16 + 16 * r) : 0.f;
     }
   }
   const float2 *tw = twt + l16;
   cp_async_wait_all();
   __syncthreads();
 
+  // skewed positions of this lane's 16 samples of frame f0 (even) and f1 (odd): the skew term
+  // is unit + a compile-time function of m
+  const int base0 = f0 * SHIFT + l16 + 16 * unit;
+#define SEP_POS_A(m) (base0 + 16 * (m) + 16 * ((16 * (m)) / SPAN))
+#define SEP_POS_B(m) (base0 + SHIFT + 16 * (m) + 16 * ((SHIFT + 16 * (m)) / SPAN))
+  const float2 *winp = reinterpret_cast<const float2 *>(win + 18 * l16);
+  const float2 *synp = reinterpret_cast<const float2 *>(syn + 18 * l16);
   float2 v[16];
 #pragma unroll
-  for (int m = 0; m < 16; ++m) {
-    v[m] = cscale(make_float2(tiles[f0 * SHIFT + l16 + 16 * m], tiles[f1 * SHIFT + l16 + 16 * m]),
-                  win[l16 + 16 * m]);
+  for (int m = 0; m < 16; m += 2) {
+    const float2 w = winp[m / 2];
+    v[m] = cscale(make_float2(tiles[SEP_POS_A(m)], tiles[SEP_POS_B(m)]), w.x);
+    v[m + 1] = cscale(make_float2(tiles[SEP_POS_A(m + 1)], tiles[SEP_POS_B(m + 1)]), w.y);
   }
-  fft256<false>(v, tw, xch, l16);
+  if (!(a.debug_skip & 8)) fft256<false>(v, tw, xch, l16);
   float2 Xa[9], Xb[9];
   split_pair(v, l16, Xa, Xb);
 
   float pit[C * C];
 #pragma unroll
   for (int i = 0; i < C * C; ++i) pit[i] = 0.f;
-  if (SCORE) {
+  if (SCORE && !(a.debug_skip & 1)) {
     const float len_f = a.lengths ? a.lengths[b] : static_cast<float>(T);
     const int len_i = static_cast<int>(len_f);
     // weights: frame counted once (owned), prediction gated by t < length (cell 28 :1031-1046)
@@ -161,11 +178,12 @@ __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedAr
     }
 #pragma unroll
     for (int j = 0; j < C; ++j) {
-      const float *ref = tiles + TILE * (1 + j);
+      const float *ref = tiles + TSK * (1 + j);
 #pragma unroll
-      for (int m = 0; m < 16; ++m) {
-        v[m] = cscale(make_float2(ref[f0 * SHIFT + l16 + 16 * m], ref[f1 * SHIFT + l16 + 16 * m]),
-                      win[l16 + 16 * m]);
+      for (int m = 0; m < 16; m += 2) {
+        const float2 w = winp[m / 2];
+        v[m] = cscale(make_float2(ref[SEP_POS_A(m)], ref[SEP_POS_B(m)]), w.x);
+        v[m + 1] = cscale(make_float2(ref[SEP_POS_A(m + 1)], ref[SEP_POS_B(m + 1)]), w.y);
       }
       fft256<false>(v, tw, xch, l16);
       float2 Sa[9], Sb[9];
@@ -188,6 +206,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedAr
   }
 
   // ---- masked spectra -> time frames -> phased overlap-add ----
+  if (!(a.debug_skip & 2))
 #pragma unroll
   for (int q = 0; q < C; ++q) {
     float2 L[9], Mi[9];
@@ -200,16 +219,22 @@ __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedAr
     }
     merge_pair(v, l16, L, Mi);
     fft256<true>(v, tw, xch, l16);
-    float *accq = acc + TILE * q;
+    float *accq = acc + TSK * q;
+#pragma unroll
+    for (int m = 0; m < 16; m += 2) {      // synthesis window on both frames at once
+      const float2 w = synp[m / 2];
+      v[m] = cscale(v[m], w.x);
+      v[m + 1] = cscale(v[m + 1], w.y);
+    }
 #pragma unroll
     for (int ph = 0; ph < R; ++ph) {
       if ((f0 % R) == ph) {
 #pragma unroll
-        for (int m = 0; m < 16; ++m) accq[f0 * SHIFT + l16 + 16 * m] += v[m].x * syn[l16 + 16 * m];
+        for (int m = 0; m < 16; ++m) accq[SEP_POS_A(m)] += v[m].x;
       }
       if ((f1 % R) == ph) {
 #pragma unroll
-        for (int m = 0; m < 16; ++m) accq[f1 * SHIFT + l16 + 16 * m] += v[m].y * syn[l16 + 16 * m];
+        for (int m = 0; m < 16; ++m) accq[SEP_POS_B(m)] += v[m].y;
       }
       __syncthreads();
     }
@@ -225,19 +250,20 @@ __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedAr
   const int span = (j1 - j0) * SHIFT;
   const int first = (j0 - t_lo) * SHIFT;                      // accumulator index of output sample 0
   const int64_t g0 = static_cast<int64_t>(j0) * SHIFT - a.pad;   // its original sample index
+  if (!(a.debug_skip & 4))
   for (int i = threadIdx.x; i < span; i += kFastThreads) {
     const int64_t g = g0 + i;
     if (g >= a.n) break;
     float e[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      e[c] = acc[TILE * c + first + i];
+      e[c] = acc[TSK * c + G::sk(first + i)];
       if (a.est) a.est[(static_cast<int64_t>(b) * C + c) * a.n + g] = e[c];
     }
     if (SCORE && g < n_valid) {
 #pragma unroll
       for (int jr = 0; jr < C; ++jr) {
-        const double r = static_cast<double>(tiles[TILE * (1 + jr) + first + i]);
+        const double r = static_cast<double>(tiles[TSK * (1 + jr) + G::sk(first + i)]);
         er[jr] = fma(r, r, er[jr]);
 #pragma unroll
         for (int ie = 0; ie < C; ++ie) gram[ie * C + jr] = fma(static_cast<double>(e[ie]), r, gram[ie * C + jr]);
@@ -249,7 +275,9 @@ __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedAr
       }
     }
   }
-  if (!SCORE) return;
+#undef SEP_POS_A
+#undef SEP_POS_B
+  if (!SCORE || (a.debug_skip & 128)) return;
   constexpr int NV = G::NV;
   double vals[NV];
 #pragma unroll
@@ -290,7 +318,8 @@ static int launch_fast(FusedArgs a, int batch, double *d_scores, double *d_sums,
   a.counters = counters;
   a.scores = d_scores;
   a.sums = d_sums;
-  a.lookahead = 148 * 3;   // one wave of resident CTAs (3 per SM)
+  a.lookahead = 148 * 3;
+  { const char *dbg = getenv("SEPCORE_DEBUG_SKIP"); a.debug_skip = dbg ? atoi(dbg) : 0; }   // one wave of resident CTAs (3 per SM)
   const size_t smem = G::smem(SCORE);
   SEP_CUDA(cudaFuncSetAttribute(fused256_kernel<C, R, SCORE>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

@@ -175,6 +175,16 @@ int sep_plan_create(sep_plan **out, int size, int shift, const double *window, i
     if ((rc = upload(&p->d_tw_half, th)) != SEP_OK) break;
     if ((rc = upload(&p->d_tw_full, tf)) != SEP_OK) break;
     if ((rc = upload(&p->d_tw16, t16)) != SEP_OK) break;
+    if (size == 256) {
+      std::vector<float> wt(16 * 18 + 8, 0.f), st(16 * 18 + 8, 0.f);
+      for (int lane = 0; lane < 16; ++lane)
+        for (int m = 0; m < 16; ++m) {
+          wt[lane * 18 + m] = wh[lane + 16 * m];
+          st[lane * 18 + m] = ws[lane + 16 * m];
+        }
+      if ((rc = upload(&p->d_win_t, wt)) != SEP_OK) break;
+      if ((rc = upload(&p->d_syn_t, st)) != SEP_OK) break;
+    }
   } while (0);
   if (rc != SEP_OK) {
     sep_plan_destroy(p);
@@ -192,6 +202,8 @@ int sep_plan_destroy(sep_plan *p) {
   cudaFree(p->d_tw_half);
   cudaFree(p->d_tw_full);
   cudaFree(p->d_tw16);
+  cudaFree(p->d_win_t);
+  cudaFree(p->d_syn_t);
   delete p;
   return SEP_OK;
 }
