@@ -212,6 +212,20 @@ int sep_conv1d_f32(const float *x, const float *kernel, const float *bias, int b
                    int rows, int c_in, int taps, int filters, int stride, int padding,
                    int activation, float *out, int mem, void *stream);
 
+/* ---- BASELINE config 5: learned conv encoder / decoder filterbank on tcgen05 ---- */
+/* A generalisation of a14 (the reference's Raw_with_Convlayer.ipynb:389 has an encoder
+ * on non-overlapping segments and no decoder): frames[k] = wave[k*stride : k*stride+taps],
+ * code = relu(frames @ enc), est_c = overlap_add((code * mask_c) @ dec, stride).
+ * wave [batch, n]; enc [taps, filters]; dec [filters, taps]; masks [batch, C, K, filters],
+ * K = (n - taps)/stride + 1  ->  est [batch, C, (K-1)*stride + taps]; code [batch, K,
+ * filters] (optional, may be NULL).  Built for taps=16, filters=256, stride=8 (tensor
+ * cores: tcgen05.mma kind::tf32 with 3xTF32 operand splitting, accumulators in TMEM);
+ * other shapes return SEP_ERR_UNSUPPORTED.  n must be a multiple of 4. */
+int sep_filterbank_separate_f32(const float *wave, const float *enc, const float *dec,
+                                const float *masks, int batch, int n_src, int64_t n_samples,
+                                int taps, int n_filters, int stride, float *est, float *code,
+                                int mem, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

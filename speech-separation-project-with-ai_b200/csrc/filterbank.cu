@@ -1,0 +1,352 @@
+// filterbank.cu -- learned 1-D conv encoder / mask / transposed-conv decoder on the
+// 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), BASELINE config 5:
+// N = 256 filters, L = 16 taps, stride 8.
+//
+// The reference's Raw_with_Convlayer (Raw_with_Convlayer.ipynb:389, cell 13) is the
+// encoder half of this idea on non-overlapping segments (served by sep_conv1d_f32);
+// BASELINE.json generalises it to the Conv-TasNet shape with a decoder, which the
+// reference does not have.  Semantics (oracle/signal_path.py: filterbank_separate):
+//   frames[k]  = wave[k*8 : k*8+16]                   K = (n - 16)/8 + 1
+//   code       = relu(frames @ enc)                   [K, 256]
+//   est_c      = overlap_add((code * mask_c) @ dec)   hop 8, length (K-1)*8 + 16
+//
+// One CTA = 128 consecutive frames of one utterance = the M = 128 rows of the MMAs;
+// thread m of the CTA owns frame row m (TMEM lane m).
+//   GEMM 1  D1[128 x 256] = A1[128 x 16] * enc           (2 k-steps of K = 8, tf32)
+//   epilogue: D1 -> registers (tcgen05.ld), relu, times mask_c, split, -> smem as the
+//             A operand of GEMM 2, 32 columns at a time, double buffered
+//   GEMM 2  D2[128 x 16]  += A2[128 x 32] * dec[32 x 16] (4 k-steps per chunk)
+//   epilogue: D2 -> registers -> overlap-add of neighbouring frames -> est
+// The masked code never touches HBM.  fp32 accuracy on a tf32 pipe: every operand is
+// split x = hi + lo with hi exactly representable in tf32, and hi*hi + lo*hi + hi*lo
+// is accumulated (3xTF32), so results agree with an fp32 reference to ~1e-6.
+//
+// Operands live in shared memory in the canonical K-major, no-swizzle UMMA layout:
+// 8-row x 16-byte core matrices; LBO = distance between the two 16-byte K chunks of one
+// MMA, SBO = distance between 8-row groups (cute/arch/mma_sm100_desc.hpp).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace sep {
+
+constexpr int kFbM = 128;        // frames per tile (MMA M)
+constexpr int kFbN = 256;        // filters
+constexpr int kFbL = 16;         // taps
+constexpr int kFbHop = 8;
+constexpr int kFbChunk = 32;     // code columns per decoder chunk
+
+// ---- shared memory map (bytes) ----
+constexpr int kA1Bytes = kFbM * kFbL * 4;            // 8 KB   [4 k-chunks][16 row groups][128 B]
+constexpr int kB1Bytes = kFbN * kFbL * 4;            // 16 KB  [4][32][128 B]
+constexpr int kB2Bytes = kFbL * kFbN * 4;            // 16 KB  [64 k-chunks][2][128 B]
+constexpr int kA2Bytes = kFbM * kFbChunk * 4;        // 16 KB  [8 k-chunks][16][128 B]
+constexpr int kOffA1Hi = 0, kOffA1Lo = kOffA1Hi + kA1Bytes;
+constexpr int kOffB1Hi = kOffA1Lo + kA1Bytes, kOffB1Lo = kOffB1Hi + kB1Bytes;
+constexpr int kOffB2Hi = kOffB1Lo + kB1Bytes, kOffB2Lo = kOffB2Hi + kB2Bytes;
+constexpr int kOffA2 = kOffB2Lo + kB2Bytes;          // 2 buffers x (hi, lo)
+constexpr int kOffUp = kOffA2 + 4 * kA2Bytes;        // [128][8] upper frame halves for the overlap-add
+constexpr int kOffBar = kOffUp + kFbM * 8 * 4;       // mbarriers + tmem address
+constexpr int kFbSmem = kOffBar + 64;
+
+constexpr uint32_t kLboA1 = 16 * 128, kLboB1 = 32 * 128, kLboB2 = 2 * 128, kLboA2 = 16 * 128, kSbo = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return static_cast<uint64_t>((addr >> 4) & 0x3FFF) | (static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16) |
+         (static_cast<uint64_t>((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);   // version 1, SWIZZLE_NONE
+}
+// kind::tf32, D = F32, A and B K-major
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
+      :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}\n"
+      :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 32 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&d)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) d[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&d)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) d[i] = __uint_as_float(r[i]);
+}
+
+// x = hi + lo with hi exactly representable in tf32 (10-bit mantissa: low 13 bits clear)
+__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  lo = x - hi;
+}
+
+// byte offset of element (row, k) in a K-major no-swizzle operand with `groups` 8-row groups
+__device__ __forceinline__ int kmajor_off(int row, int k, int groups) {
+  return (k >> 2) * groups * 128 + (row >> 3) * 128 + (row & 7) * 16 + (k & 3) * 4;
+}
+
+struct FbArgs {
+  const float *wave, *enc, *dec, *masks;
+  float *est, *code;
+  int64_t n, est_len;
+  int n_src, frames, tiles;
+};
+
+__global__ void __launch_bounds__(128, 1) filterbank_kernel(const FbArgs a) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  const int m = threadIdx.x, warp = m >> 5;
+  const int b = blockIdx.y, tile = blockIdx.x;
+  const int k0 = tile * (kFbM - 1);                     // first frame of the tile (1-frame halo)
+  const int K = a.frames;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sm + kOffBar);     // [0] gemm1, [1..2] a2 buffers free, [3] d2 ready
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + kOffBar + 32);
+  const uint32_t bar0 = smem_u32(bars), sm0 = smem_u32(sm);
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (m == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(bar0 + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+
+  // ---- operands of GEMM 1 and the decoder weights, split hi / lo, canonical layout ----
+  for (int e = m; e < kFbL * kFbN; e += 128) {
+    // enc [L][N] row-major -> B1[n][k = l];  dec [N][L] row-major -> B2[n2 = l][k = n]
+    const int l = e / kFbN, nn = e % kFbN;
+    float hi, lo;
+    split_tf32(__ldg(a.enc + e), hi, lo);
+    const int o1 = kmajor_off(nn, l, kFbN / 8);
+    *reinterpret_cast<float *>(sm + kOffB1Hi + o1) = hi;
+    *reinterpret_cast<float *>(sm + kOffB1Lo + o1) = lo;
+    const int nf = e / kFbL, ll = e % kFbL;
+    split_tf32(__ldg(a.dec + e), hi, lo);
+    const int o2 = kmajor_off(ll, nf, kFbL / 8);
+    *reinterpret_cast<float *>(sm + kOffB2Hi + o2) = hi;
+    *reinterpret_cast<float *>(sm + kOffB2Lo + o2) = lo;
+  }
+  {
+    const int frame = k0 + m;
+    const float *src = a.wave + static_cast<int64_t>(b) * a.n + static_cast<int64_t>(frame) * kFbHop;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {                    // 4 k-chunks of 4 taps
+      float4 hi, lo;
+      float x[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) x[i] = frame < K ? __ldg(src + 4 * q + i) : 0.f;
+      split_tf32(x[0], hi.x, lo.x); split_tf32(x[1], hi.y, lo.y);
+      split_tf32(x[2], hi.z, lo.z); split_tf32(x[3], hi.w, lo.w);
+      const int o = q * (kFbM / 8) * 128 + (m >> 3) * 128 + (m & 7) * 16;
+      *reinterpret_cast<float4 *>(sm + kOffA1Hi + o) = hi;
+      *reinterpret_cast<float4 *>(sm + kOffA1Lo + o) = lo;
+    }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_addr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+
+  // ---- GEMM 1: D1 = A1 * enc, 3xTF32 ----
+  if (m == 0) {
+    constexpr uint32_t idesc = umma_idesc_tf32(kFbM, kFbN);
+    uint32_t acc = 0;
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {           // hi*hi, lo*hi, hi*lo
+      const uint32_t aoff = sm0 + (pass == 1 ? kOffA1Lo : kOffA1Hi);
+      const uint32_t boff = sm0 + (pass == 2 ? kOffB1Lo : kOffB1Hi);
+#pragma unroll
+      for (int ks = 0; ks < kFbL / 8; ++ks) {
+        umma_tf32(tmem, umma_desc(aoff + ks * 2 * kLboA1, kLboA1, kSbo),
+                  umma_desc(boff + ks * 2 * kLboB1, kLboB1, kSbo), idesc, acc);
+        acc = 1;
+      }
+    }
+    umma_commit(bar0);
+  }
+  mbar_wait(bar0, 0);
+  tc_fence_after();
+
+  // ---- per source: relu * mask -> GEMM 2 in 32-column chunks -> overlap-add ----
+  const int frame = k0 + m;
+  const bool row_ok = frame < K;
+  const bool owner = row_ok && (m > 0 || tile == 0);   // row 0 of a later tile is the halo frame
+  int use[2] = {0, 0};                               // how often each A2 buffer has been filled
+  for (int c = 0; c < a.n_src; ++c) {
+    const float *mrow = a.masks + ((static_cast<int64_t>(b) * a.n_src + c) * K + (row_ok ? frame : 0)) * kFbN;
+    for (int j = 0; j < kFbN / kFbChunk; ++j) {
+      float d[32];
+      tmem_ld32(lane_addr + j * kFbChunk, d);
+      const int buf = j & 1;
+      if (use[buf] > 0) mbar_wait(bar0 + 8 * (1 + buf), (use[buf] - 1) & 1);   // MMAs that read it are done
+      unsigned char *a2hi = sm + kOffA2 + buf * 2 * kA2Bytes, *a2lo = a2hi + kA2Bytes;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 mk = row_ok ? __ldg(reinterpret_cast<const float4 *>(mrow + j * kFbChunk) + q)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        float v[4] = {fmaxf(d[4 * q], 0.f), fmaxf(d[4 * q + 1], 0.f), fmaxf(d[4 * q + 2], 0.f),
+                      fmaxf(d[4 * q + 3], 0.f)};
+        if (c == 0 && a.code && owner)
+          *reinterpret_cast<float4 *>(a.code + (static_cast<int64_t>(b) * K + frame) * kFbN + j * kFbChunk + 4 * q) =
+              make_float4(v[0], v[1], v[2], v[3]);
+        float4 hi, lo;
+        split_tf32(v[0] * mk.x, hi.x, lo.x); split_tf32(v[1] * mk.y, hi.y, lo.y);
+        split_tf32(v[2] * mk.z, hi.z, lo.z); split_tf32(v[3] * mk.w, hi.w, lo.w);
+        const int o = q * (kFbM / 8) * 128 + (m >> 3) * 128 + (m & 7) * 16;
+        *reinterpret_cast<float4 *>(a2hi + o) = hi;
+        *reinterpret_cast<float4 *>(a2lo + o) = lo;
+      }
+      ++use[buf];
+      fence_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      if (m == 0) {
+        constexpr uint32_t idesc = umma_idesc_tf32(kFbM, kFbL);
+        const uint32_t a2 = sm0 + kOffA2 + buf * 2 * kA2Bytes;
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t aoff = a2 + (pass == 1 ? kA2Bytes : 0);
+          const uint32_t boff = sm0 + (pass == 2 ? kOffB2Lo : kOffB2Hi) + j * (kFbChunk / 4) * kLboB2;
+#pragma unroll
+          for (int ks = 0; ks < kFbChunk / 8; ++ks)
+            umma_tf32(tmem + kFbN, umma_desc(aoff + ks * 2 * kLboA2, kLboA2, kSbo),
+                      umma_desc(boff + ks * 2 * kLboB2, kLboB2, kSbo), idesc,
+                      (j | pass | ks) != 0 ? 1u : 0u);
+        }
+        umma_commit(bar0 + 8 * (1 + buf));
+        if (j == kFbN / kFbChunk - 1) umma_commit(bar0 + 8 * 3);
+      }
+    }
+    mbar_wait(bar0 + 8 * 3, c & 1);
+    tc_fence_after();
+    float y[16];
+    tmem_ld16(lane_addr + kFbN, y);
+    // overlap-add: hop-block h = frame gets y[frame][0:8] + y[frame-1][8:16]
+    float *up = reinterpret_cast<float *>(sm + kOffUp);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) up[m * 8 + i] = y[8 + i];
+    tc_fence_before();
+    __syncthreads();
+    float *out = a.est + (static_cast<int64_t>(b) * a.n_src + c) * a.est_len;
+    if (owner) {
+      float4 lo4 = make_float4(y[0], y[1], y[2], y[3]), hi4 = make_float4(y[4], y[5], y[6], y[7]);
+      if (m > 0) {
+        const float *p = up + (m - 1) * 8;
+        lo4.x += p[0]; lo4.y += p[1]; lo4.z += p[2]; lo4.w += p[3];
+        hi4.x += p[4]; hi4.y += p[5]; hi4.z += p[6]; hi4.w += p[7];
+      }
+      float4 *dst = reinterpret_cast<float4 *>(out + static_cast<int64_t>(frame) * kFbHop);
+      dst[0] = lo4;
+      dst[1] = hi4;
+    }
+    if (owner && frame == K - 1) {                     // the tail hop-block of the utterance
+      float4 *dst = reinterpret_cast<float4 *>(out + static_cast<int64_t>(K) * kFbHop);
+      dst[0] = make_float4(y[8], y[9], y[10], y[11]);
+      dst[1] = make_float4(y[12], y[13], y[14], y[15]);
+    }
+    __syncthreads();                                  // `up` and D2 are reused by the next source
+    tc_fence_after();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u));
+}
+
+}  // namespace sep
+
+using namespace sep;
+
+extern "C" int sep_filterbank_separate_f32(const float *wave, const float *enc, const float *dec,
+                                           const float *masks, int batch, int n_src, int64_t n_samples,
+                                           int taps, int n_filters, int stride, float *est, float *code,
+                                           int mem, void *stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SEP_REQUIRE(wave && enc && dec && masks && est, "sep_filterbank_separate_f32: null argument");
+  SEP_REQUIRE(batch >= 1 && n_src >= 1 && n_src <= SEP_MAX_SOURCES && n_samples >= taps,
+              "sep_filterbank_separate_f32: bad shape");
+  if (taps != kFbL || n_filters != kFbN || stride != kFbHop) {
+    set_error("sep_filterbank_separate_f32: only L=%d, N=%d, stride=%d is built (got L=%d N=%d stride=%d)",
+              kFbL, kFbN, kFbHop, taps, n_filters, stride);
+    return SEP_ERR_UNSUPPORTED;
+  }
+  SEP_REQUIRE(n_samples % 4 == 0, "sep_filterbank_separate_f32: n_samples must be a multiple of 4");
+  int rc = check_mem(mem);
+  if (rc) return rc;
+  const int64_t K = (n_samples - taps) / stride + 1;
+  const int64_t est_len = (K - 1) * stride + taps;
+  Scratch s(stream);
+  FbArgs a{};
+  const size_t n_mask = static_cast<size_t>(batch) * n_src * K * n_filters;
+  const size_t n_est = static_cast<size_t>(batch) * n_src * est_len, n_code = static_cast<size_t>(batch) * K * n_filters;
+  if ((rc = stage_in(s, wave, static_cast<size_t>(batch) * n_samples, mem, &a.wave))) return rc;
+  if ((rc = stage_in(s, enc, static_cast<size_t>(taps) * n_filters, mem, &a.enc))) return rc;
+  if ((rc = stage_in(s, dec, static_cast<size_t>(taps) * n_filters, mem, &a.dec))) return rc;
+  if ((rc = stage_in(s, masks, n_mask, mem, &a.masks))) return rc;
+  if ((rc = stage_out(s, est, n_est, mem, &a.est))) return rc;
+  if ((rc = stage_out(s, code, n_code, mem, &a.code))) return rc;
+  a.n = n_samples;
+  a.est_len = est_len;
+  a.n_src = n_src;
+  a.frames = static_cast<int>(K);
+  // tile t owns frames 127 t + 1 .. 127 t + 127 (and frame 0 for t = 0)
+  a.tiles = static_cast<int>(std::max<int64_t>(1, (K - 1 + kFbM - 2) / (kFbM - 1)));
+  SEP_CUDA(cudaFuncSetAttribute(filterbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFbSmem));
+  dim3 grid(a.tiles, batch);
+  profile_begin(stream);
+  filterbank_kernel<<<grid, 128, kFbSmem, stream>>>(a);
+  profile_end(stream);
+  SEP_LAUNCHED();
+  if ((rc = copy_back(s, est, a.est, n_est, mem))) return rc;
+  if ((rc = copy_back(s, code, a.code, n_code, mem))) return rc;
+  return finish(s, mem);
+}

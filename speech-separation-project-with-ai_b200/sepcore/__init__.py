@@ -14,7 +14,7 @@ from .signal_path import (_biorthogonal_window_loopy, _samples_to_stft_frames,
 from .losses import pit_mse, pit_with_outputsize
 from .scoring import (permute_si_sdr, pow_norm, pow_np_norm, score_batch, score_flat_device, si_sdr,
                       truncate_to_min_len)
-from .filterbank import conv1d, segment_raw
+from .filterbank import conv1d, filterbank_separate, segment_raw
 from .fused import parse_scores, score_layout, separate_and_score, workspace_bytes
 from .graphs import GraphedSeparator
 from .pipeline import HostPipeline
@@ -26,7 +26,7 @@ __all__ = [
     "_biorthogonal_window_loopy", "istft", "recombine_istft",
     "pit_mse", "pit_with_outputsize",
     "pow_np_norm", "pow_norm", "si_sdr", "permute_si_sdr", "score_batch", "score_flat_device",
-    "truncate_to_min_len", "conv1d", "segment_raw",
+    "truncate_to_min_len", "conv1d", "segment_raw", "filterbank_separate",
     "separate_and_score", "score_layout", "parse_scores", "workspace_bytes", "GraphedSeparator", "HostPipeline",
     "distributed",
 ]

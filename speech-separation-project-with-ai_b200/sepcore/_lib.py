@@ -59,6 +59,8 @@ PROTOTYPES = {
     "sep_score_batch_f32": (_int, [_vp, _vp, _i64p, _i64p, _i64p, _int, _int, _i64, _i64, _vp, _vp,
                                    _int, _vp]),
     "sep_dot_f32": (_int, [_vp, _vp, _i64, _vp, _int, _vp]),
+    "sep_filterbank_separate_f32": (_int, [_vp, _vp, _vp, _vp, _int, _int, _i64, _int, _int, _int, _vp,
+                                           _vp, _int, _vp]),
     "sep_conv1d_f32": (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _int, _vp,
                               _int, _vp]),
 }

@@ -472,3 +472,29 @@ def test_single_launch_finalisation_matches(sep, oracle, monkeypatch):
         subprocess.run([sys.executable, "-c", code, path], check=True, env=env)
         outs.append(np.load(path))
     assert np.array_equal(outs[0], outs[1])
+
+
+# ----------------------------------------------------------------- cfg5: tcgen05 filterbank
+@pytest.mark.parametrize("n,n_src", [(1040, 1), (2000, 2), (32000, 2), (16 + 8 * 127, 3), (16 + 8 * 254, 2)])
+def test_filterbank_tcgen05_matches_oracle(sep, oracle, n, n_src):
+    """Encoder -> relu -> mask -> decoder -> overlap-add on the tensor cores (3xTF32) against
+    the float64 oracle: fp32-level agreement (1e-4 of the array scale, 1e-5 relative L2)."""
+    rng = np.random.default_rng(n + n_src)
+    batch, taps, filters, stride = 2, 16, 256, 8
+    wave = (0.1 * rng.standard_normal((batch, n))).astype(np.float32)
+    enc = (0.25 * rng.standard_normal((taps, filters))).astype(np.float32)
+    dec = (0.06 * rng.standard_normal((filters, taps))).astype(np.float32)
+    frames = (n - taps) // stride + 1
+    masks = rng.random((batch, n_src, frames, filters)).astype(np.float32)
+    est, code = sep.filterbank_separate(wave, enc, dec, masks, stride=stride, want_code=True)
+    for b in range(batch):
+        want_code, want_est = oracle.filterbank_separate(wave[b], enc, dec, masks[b], stride)
+        assert code[b].shape == want_code.shape and est[b].shape == want_est.shape
+        assert rel_err(code[b], want_code) < TOL_REL and rel_l2(code[b], want_code) < 1e-5
+        assert rel_err(est[b], want_est) < TOL_REL and rel_l2(est[b], want_est) < 1e-5
+
+
+def test_filterbank_unsupported_shape(sep):
+    with pytest.raises(NotImplementedError):
+        sep.filterbank_separate(np.zeros((1, 400), np.float32), np.zeros((20, 64), np.float32),
+                                np.zeros((64, 20), np.float32), np.zeros((1, 1, 39, 64), np.float32), stride=10)
