@@ -47,7 +47,10 @@ constexpr int kOffB2Hi = kOffB1Lo + kB1Bytes, kOffB2Lo = kOffB2Hi + kB2Bytes;
 constexpr int kOffA2 = kOffB2Lo + kB2Bytes;          // 2 buffers x (hi, lo)
 constexpr int kOffUp = kOffA2 + 4 * kA2Bytes;        // [128][8] upper frame halves for the overlap-add
 constexpr int kOffBar = kOffUp + kFbM * 8 * 4;       // mbarriers + tmem address
-constexpr int kFbSmem = kOffBar + 64;
+constexpr int kFbStages = 4;                         // mask tiles in flight (cp.async ring)
+constexpr int kMaskTile = kFbM * kFbChunk * 4;       // 16 KB  [8 float4 columns][128 rows][16 B]
+constexpr int kOffMask = kOffBar + 64;
+constexpr int kFbSmem = kOffMask + kFbStages * kMaskTile;
 
 constexpr uint32_t kLboA1 = 16 * 128, kLboB1 = 32 * 128, kLboB2 = 2 * 128, kLboA2 = 16 * 128, kSbo = 128;
 
@@ -134,14 +137,12 @@ struct FbArgs {
   const float *wave, *enc, *dec, *masks;
   float *est, *code;
   int64_t n, est_len;
-  int n_src, frames, tiles;
+  int n_src, frames, tiles, batch;
 };
 
 __global__ void __launch_bounds__(128, 1) filterbank_kernel(const FbArgs a) {
   extern __shared__ __align__(128) unsigned char sm[];
   const int m = threadIdx.x, warp = m >> 5;
-  const int b = blockIdx.y, tile = blockIdx.x;
-  const int k0 = tile * (kFbM - 1);                     // first frame of the tile (1-frame halo)
   const int K = a.frames;
   uint64_t *bars = reinterpret_cast<uint64_t *>(sm + kOffBar);     // [0] gemm1, [1..2] a2 buffers free, [3] d2 ready
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + kOffBar + 32);
@@ -157,20 +158,41 @@ __global__ void __launch_bounds__(128, 1) filterbank_kernel(const FbArgs a) {
   }
 
   // ---- operands of GEMM 1 and the decoder weights, split hi / lo, canonical layout ----
-  for (int e = m; e < kFbL * kFbN; e += 128) {
-    // enc [L][N] row-major -> B1[n][k = l];  dec [N][L] row-major -> B2[n2 = l][k = n]
-    const int l = e / kFbN, nn = e % kFbN;
-    float hi, lo;
-    split_tf32(__ldg(a.enc + e), hi, lo);
-    const int o1 = kmajor_off(nn, l, kFbN / 8);
-    *reinterpret_cast<float *>(sm + kOffB1Hi + o1) = hi;
-    *reinterpret_cast<float *>(sm + kOffB1Lo + o1) = lo;
-    const int nf = e / kFbL, ll = e % kFbL;
-    split_tf32(__ldg(a.dec + e), hi, lo);
-    const int o2 = kmajor_off(ll, nf, kFbL / 8);
-    *reinterpret_cast<float *>(sm + kOffB2Hi + o2) = hi;
-    *reinterpret_cast<float *>(sm + kOffB2Lo + o2) = lo;
+  // (once per CTA: the kernel is persistent over tiles)
+#pragma unroll 1
+  for (int e0 = 0; e0 < kFbL * kFbN; e0 += 128 * 8) {
+    float we[8], wd[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {                      // all loads first: one L2 latency per 8 elements
+      we[u] = __ldg(a.enc + e0 + 128 * u + m);
+      wd[u] = __ldg(a.dec + e0 + 128 * u + m);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      // enc [L][N] row-major -> B1[n][k = l];  dec [N][L] row-major -> B2[n2 = l][k = n]
+      const int e = e0 + 128 * u + m;
+      const int l = e / kFbN, nn = e % kFbN;
+      float hi, lo;
+      split_tf32(we[u], hi, lo);
+      const int o1 = kmajor_off(nn, l, kFbN / 8);
+      *reinterpret_cast<float *>(sm + kOffB1Hi + o1) = hi;
+      *reinterpret_cast<float *>(sm + kOffB1Lo + o1) = lo;
+      const int nf = e / kFbL, ll = e % kFbL;
+      split_tf32(wd[u], hi, lo);
+      const int o2 = kmajor_off(ll, nf, kFbL / 8);
+      *reinterpret_cast<float *>(sm + kOffB2Hi + o2) = hi;
+      *reinterpret_cast<float *>(sm + kOffB2Lo + o2) = lo;
+    }
   }
+  __syncthreads();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_addr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  int use[2] = {0, 0};                               // how often each A2 buffer has been filled
+  uint32_t round = 0;                                // tiles done by this CTA (mbarrier phase)
+
+  for (int t = blockIdx.x; t < a.tiles * a.batch; t += gridDim.x, ++round) {
+  const int b = t / a.tiles, tile = t - b * a.tiles;
+  const int k0 = tile * (kFbM - 1);                     // first frame of the tile (1-frame halo)
   {
     const int frame = k0 + m;
     const float *src = a.wave + static_cast<int64_t>(b) * a.n + static_cast<int64_t>(frame) * kFbHop;
@@ -191,8 +213,6 @@ __global__ void __launch_bounds__(128, 1) filterbank_kernel(const FbArgs a) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t lane_addr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
 
   // ---- GEMM 1: D1 = A1 * enc, 3xTF32 ----
   if (m == 0) {
@@ -211,71 +231,94 @@ __global__ void __launch_bounds__(128, 1) filterbank_kernel(const FbArgs a) {
     }
     umma_commit(bar0);
   }
-  mbar_wait(bar0, 0);
+  mbar_wait(bar0, round & 1);
   tc_fence_after();
 
-  // ---- per source: relu * mask -> GEMM 2 in 32-column chunks -> overlap-add ----
+  // ---- relu * mask_c -> GEMM 2, 32 code columns at a time, all sources per chunk ----
+  // Work items g = (chunk j, source c).  The 16 KB mask tile of item g is fetched with
+  // cp.async kFbStages - 1 items ahead (each thread stages and later reads only its own
+  // row, so the ring needs no block barrier); the masked code goes to one of two A2
+  // buffers; thread 0 issues the decoder MMAs of item g while everybody prepares g + 1.
   const int frame = k0 + m;
   const bool row_ok = frame < K;
   const bool owner = row_ok && (m > 0 || tile == 0);   // row 0 of a later tile is the halo frame
-  int use[2] = {0, 0};                               // how often each A2 buffer has been filled
-  for (int c = 0; c < a.n_src; ++c) {
-    const float *mrow = a.masks + ((static_cast<int64_t>(b) * a.n_src + c) * K + (row_ok ? frame : 0)) * kFbN;
-    for (int j = 0; j < kFbN / kFbChunk; ++j) {
-      float d[32];
+  const int C = a.n_src, G = (kFbN / kFbChunk) * C;
+  const float *mbase = a.masks + (static_cast<int64_t>(b) * C * K + (row_ok ? frame : 0)) * kFbN;
+  auto stage_masks = [&](int g) {
+    if (g < G && row_ok) {
+      const int j = g / C, c = g - j * C;
+      const float *src = mbase + static_cast<int64_t>(c) * K * kFbN + j * kFbChunk;
+      unsigned char *dst = sm + kOffMask + (g % kFbStages) * kMaskTile + m * 16;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) cp_async16(dst + q * (kFbM * 16), src + 4 * q);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int g = 0; g < kFbStages - 1; ++g) stage_masks(g);
+  float d[32];
+  for (int g = 0; g < G; ++g) {
+    const int j = g / C, c = g - j * C;
+    if (c == 0) {
       tmem_ld32(lane_addr + j * kFbChunk, d);
-      const int buf = j & 1;
-      if (use[buf] > 0) mbar_wait(bar0 + 8 * (1 + buf), (use[buf] - 1) & 1);   // MMAs that read it are done
-      unsigned char *a2hi = sm + kOffA2 + buf * 2 * kA2Bytes, *a2lo = a2hi + kA2Bytes;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 mk = row_ok ? __ldg(reinterpret_cast<const float4 *>(mrow + j * kFbChunk) + q)
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-        float v[4] = {fmaxf(d[4 * q], 0.f), fmaxf(d[4 * q + 1], 0.f), fmaxf(d[4 * q + 2], 0.f),
-                      fmaxf(d[4 * q + 3], 0.f)};
-        if (c == 0 && a.code && owner)
-          *reinterpret_cast<float4 *>(a.code + (static_cast<int64_t>(b) * K + frame) * kFbN + j * kFbChunk + 4 * q) =
-              make_float4(v[0], v[1], v[2], v[3]);
-        float4 hi, lo;
-        split_tf32(v[0] * mk.x, hi.x, lo.x); split_tf32(v[1] * mk.y, hi.y, lo.y);
-        split_tf32(v[2] * mk.z, hi.z, lo.z); split_tf32(v[3] * mk.w, hi.w, lo.w);
-        const int o = q * (kFbM / 8) * 128 + (m >> 3) * 128 + (m & 7) * 16;
-        *reinterpret_cast<float4 *>(a2hi + o) = hi;
-        *reinterpret_cast<float4 *>(a2lo + o) = lo;
-      }
-      ++use[buf];
-      fence_async_smem();
-      tc_fence_before();
-      __syncthreads();
-      tc_fence_after();
-      if (m == 0) {
-        constexpr uint32_t idesc = umma_idesc_tf32(kFbM, kFbL);
-        const uint32_t a2 = sm0 + kOffA2 + buf * 2 * kA2Bytes;
+      for (int i = 0; i < 32; ++i) d[i] = fmaxf(d[i], 0.f);
+      if (a.code && owner) {
+        float4 *dst = reinterpret_cast<float4 *>(a.code + (static_cast<int64_t>(b) * K + frame) * kFbN + j * kFbChunk);
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t aoff = a2 + (pass == 1 ? kA2Bytes : 0);
-          const uint32_t boff = sm0 + (pass == 2 ? kOffB2Lo : kOffB2Hi) + j * (kFbChunk / 4) * kLboB2;
-#pragma unroll
-          for (int ks = 0; ks < kFbChunk / 8; ++ks)
-            umma_tf32(tmem + kFbN, umma_desc(aoff + ks * 2 * kLboA2, kLboA2, kSbo),
-                      umma_desc(boff + ks * 2 * kLboB2, kLboB2, kSbo), idesc,
-                      (j | pass | ks) != 0 ? 1u : 0u);
-        }
-        umma_commit(bar0 + 8 * (1 + buf));
-        if (j == kFbN / kFbChunk - 1) umma_commit(bar0 + 8 * 3);
+        for (int q = 0; q < 8; ++q) dst[q] = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
       }
     }
-    mbar_wait(bar0 + 8 * 3, c & 1);
+    stage_masks(g + kFbStages - 1);
+    asm volatile("cp.async.wait_group %0;" :: "n"(kFbStages - 1) : "memory");
+    const int buf = g & 1;
+    if (use[buf] > 0) mbar_wait(bar0 + 8 * (1 + buf), (use[buf] - 1) & 1);   // MMAs that read it are done
+    unsigned char *a2hi = sm + kOffA2 + buf * 2 * kA2Bytes, *a2lo = a2hi + kA2Bytes;
+    const unsigned char *mk_s = sm + kOffMask + (g % kFbStages) * kMaskTile + m * 16;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 mk = row_ok ? *reinterpret_cast<const float4 *>(mk_s + q * (kFbM * 16))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 hi, lo;
+      split_tf32(d[4 * q] * mk.x, hi.x, lo.x); split_tf32(d[4 * q + 1] * mk.y, hi.y, lo.y);
+      split_tf32(d[4 * q + 2] * mk.z, hi.z, lo.z); split_tf32(d[4 * q + 3] * mk.w, hi.w, lo.w);
+      const int o = q * (kFbM / 8) * 128 + (m >> 3) * 128 + (m & 7) * 16;
+      *reinterpret_cast<float4 *>(a2hi + o) = hi;
+      *reinterpret_cast<float4 *>(a2lo + o) = lo;
+    }
+    ++use[buf];
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
     tc_fence_after();
+    if (m == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(kFbM, kFbL);
+      const uint32_t a2 = sm0 + kOffA2 + buf * 2 * kA2Bytes;
+#pragma unroll
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t aoff = a2 + (pass == 1 ? kA2Bytes : 0);
+        const uint32_t boff = sm0 + (pass == 2 ? kOffB2Lo : kOffB2Hi) + j * (kFbChunk / 4) * kLboB2;
+#pragma unroll
+        for (int ks = 0; ks < kFbChunk / 8; ++ks)
+          umma_tf32(tmem + kFbN + kFbL * c, umma_desc(aoff + ks * 2 * kLboA2, kLboA2, kSbo),
+                    umma_desc(boff + ks * 2 * kLboB2, kLboB2, kSbo), idesc, (j | pass | ks) != 0 ? 1u : 0u);
+      }
+      umma_commit(bar0 + 8 * (1 + buf));
+      if (g == G - 1) umma_commit(bar0 + 8 * 3);
+    }
+  }
+  mbar_wait(bar0 + 8 * 3, round & 1);
+  tc_fence_after();
+
+  // ---- D2_c -> registers -> overlap-add of neighbouring frames -> est ----
+  for (int c = 0; c < C; ++c) {
     float y[16];
-    tmem_ld16(lane_addr + kFbN, y);
-    // overlap-add: hop-block h = frame gets y[frame][0:8] + y[frame-1][8:16]
+    tmem_ld16(lane_addr + kFbN + kFbL * c, y);
+    // hop-block h = frame gets y[frame][0:8] + y[frame-1][8:16]
     float *up = reinterpret_cast<float *>(sm + kOffUp);
 #pragma unroll
     for (int i = 0; i < 8; ++i) up[m * 8 + i] = y[8 + i];
-    tc_fence_before();
     __syncthreads();
-    float *out = a.est + (static_cast<int64_t>(b) * a.n_src + c) * a.est_len;
+    float *out = a.est + (static_cast<int64_t>(b) * C + c) * a.est_len;
     if (owner) {
       float4 lo4 = make_float4(y[0], y[1], y[2], y[3]), hi4 = make_float4(y[4], y[5], y[6], y[7]);
       if (m > 0) {
@@ -286,15 +329,15 @@ __global__ void __launch_bounds__(128, 1) filterbank_kernel(const FbArgs a) {
       float4 *dst = reinterpret_cast<float4 *>(out + static_cast<int64_t>(frame) * kFbHop);
       dst[0] = lo4;
       dst[1] = hi4;
+      if (frame == K - 1) {                              // the tail hop-block of the utterance
+        dst[2] = make_float4(y[8], y[9], y[10], y[11]);
+        dst[3] = make_float4(y[12], y[13], y[14], y[15]);
+      }
     }
-    if (owner && frame == K - 1) {                     // the tail hop-block of the utterance
-      float4 *dst = reinterpret_cast<float4 *>(out + static_cast<int64_t>(K) * kFbHop);
-      dst[0] = make_float4(y[8], y[9], y[10], y[11]);
-      dst[1] = make_float4(y[12], y[13], y[14], y[15]);
-    }
-    __syncthreads();                                  // `up` and D2 are reused by the next source
-    tc_fence_after();
+    __syncthreads();                                    // `up` is reused by the next source
   }
+  tc_fence_before();                                    // D1 / D2 are overwritten by the next tile
+  }  // tile loop
 
   tc_fence_before();
   __syncthreads();
@@ -337,11 +380,16 @@ extern "C" int sep_filterbank_separate_f32(const float *wave, const float *enc, 
   a.n = n_samples;
   a.est_len = est_len;
   a.n_src = n_src;
+  a.batch = batch;
   a.frames = static_cast<int>(K);
   // tile t owns frames 127 t + 1 .. 127 t + 127 (and frame 0 for t = 0)
   a.tiles = static_cast<int>(std::max<int64_t>(1, (K - 1 + kFbM - 2) / (kFbM - 1)));
   SEP_CUDA(cudaFuncSetAttribute(filterbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFbSmem));
-  dim3 grid(a.tiles, batch);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // persistent: one CTA per SM (its 200+ KB of shared memory and 512 TMEM columns fill the SM)
+  dim3 grid(static_cast<unsigned>(std::min<int64_t>(static_cast<int64_t>(a.tiles) * batch, sms)));
   profile_begin(stream);
   filterbank_kernel<<<grid, 128, kFbSmem, stream>>>(a);
   profile_end(stream);
