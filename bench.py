@@ -383,7 +383,7 @@ def run_sepcore(args):
                                       % world},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "fused256_kernel (timed alone, one launch at a time, CUDA events "
+                         "kernel": "dominant fused kernel (strip256_kernel at 256/{128,64}, C<=2) (timed alone, one launch at a time, CUDA events "
                                    "around the launch on its stream)",
                          "kernel_ms": kernel_ms_avg, "bytes_per_launch": bytes_per_launch,
                          "launches_timed": bracketed,

@@ -134,4 +134,53 @@ __device__ __forceinline__ void merge_pair(float2 (&v)[16], int l16, const float
   }
 }
 
+
+// ---- variant with 128-bit shared-memory reads (fused_strip.cu) ----
+// Transpose rows and the per-lane twiddle rows have a pitch of 18 float2: a lane's 16
+// values are contiguous and 16-byte aligned (8 LDS.128 instead of 16 LDS.64), and the 8
+// lanes of a quarter-warp land on 8 distinct 16-byte bank groups (36 l mod 32 = 4 l).
+constexpr int kXchPitchV = 18;
+constexpr int kXchFloat2V = 16 * kXchPitchV;     // per half-warp
+
+// twl: this lane's twiddle row, twl[j] = exp(-2 pi i * l16 * j / 256), j = 0..15.
+template <bool INV>
+__device__ __forceinline__ void fft256v(float2 (&v)[16], const float2 *twl, float2 *xch, int l16) {
+  fft16<INV>(v);
+  const float4 *tw4 = reinterpret_cast<const float4 *>(twl);
+#pragma unroll
+  for (int j = 0; j < 16; j += 2) {
+    const float4 w = tw4[j / 2];
+    if (j > 0) v[j] = cmul(v[j], make_float2(w.x, INV ? -w.y : w.y));
+    v[j + 1] = cmul(v[j + 1], make_float2(w.z, INV ? -w.w : w.w));
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) xch[j * kXchPitchV + l16] = v[j];
+  __syncwarp();
+  const float4 *row = reinterpret_cast<const float4 *>(xch + l16 * kXchPitchV);
+#pragma unroll
+  for (int q = 0; q < 16; q += 2) {
+    const float4 t = row[q / 2];
+    v[q] = make_float2(t.x, t.y);
+    v[q + 1] = make_float2(t.z, t.w);
+  }
+  fft16<INV>(v);
+}
+
+// Planar split: after a forward transform of z = a + i b, XR[r] = (Re A, Re B) and
+// XI[r] = (Im A, Im B) at this lane's bins l16 + 16 r -- the same two packed adds as
+// split_pair, but frames a and b side by side so that everything downstream (|X|, labels,
+// squared differences, mask multiply) runs on packed pairs.
+__device__ __forceinline__ void split_planar(const float2 (&v)[16], int l16, int r, float2 &XR, float2 &XI) {
+  const int src = (16 - l16) & 15;
+  float2 got;
+  got.x = __shfl_sync(0xffffffffu, v[r < 8 ? 15 - r : 7].x, src, 16);
+  got.y = __shfl_sync(0xffffffffu, v[r < 8 ? 15 - r : 7].y, src, 16);
+  const float2 own = v[(16 - r) & 15];
+  const float2 zp = (l16 == 0) ? own : got;
+  const float2 z = v[r];
+  XR = __fadd2_rn(z, zp);                                                  // (zx + z'x, zy + z'y)
+  XI = __fadd2_rn(make_float2(z.y, -z.x), make_float2(-zp.y, zp.x));       // (zy - z'y, z'x - zx)
+}
+
 }  // namespace sep

@@ -330,7 +330,8 @@ extern "C" int sep_fused_separate_ws_f32(const sep_plan *p, const float *mix, co
   a.syn_t = p->d_syn_t;
 
   bool handled = false;
-  if ((rc = fused_fast_try(p, a, batch, C, d_scores, d_sums, s, stream, &handled))) return rc;
+  if ((rc = fused_strip_try(p, a, batch, C, d_scores, d_sums, s, stream, &handled))) return rc;
+  if (!handled && (rc = fused_fast_try(p, a, batch, C, d_scores, d_sums, s, stream, &handled))) return rc;
   if (!handled) {
     switch (C) {
       case 1: rc = run_fused<1>(p, a, batch, d_scores, d_sums, s, stream); break;

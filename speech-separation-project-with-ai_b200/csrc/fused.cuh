@@ -21,6 +21,7 @@ struct FusedArgs {
   int T, size, shift, pad, tb, tiles;
   int debug_skip;   // developer timing aid (SEPCORE_DEBUG_SKIP): bit0 refs+PIT, bit1 inverse+OLA, bit2 gather, bit3 mix FFT
   int batch, lookahead;   // lookahead: tiles ahead of this CTA to pull into L2 (0 = off)
+  int strip_iters, vec_ok;  // strip kernel: iterations per utterance; rows 16-byte aligned
   const float *win_half, *syn;
   const float *win_t, *syn_t;   // [16][18] transposed tables (size 256)
   const float2 *tw_half, *tw_full, *tw16;
@@ -150,6 +151,8 @@ static int launch_fused_finalize(const FusedArgs &a, int batch, double *d_scores
 
 // Register-resident 256/512-point specialisation (fused_fast.cu).  Sets *handled when it
 // launched; otherwise the generic kernel runs.
+int fused_strip_try(const sep_plan *p, const FusedArgs &a, int batch, int C, double *d_scores,
+                    double *d_sums, Scratch &s, cudaStream_t stream, bool *handled);
 int fused_fast_try(const sep_plan *p, const FusedArgs &a, int batch, int C, double *d_scores,
                    double *d_sums, Scratch &s, cudaStream_t stream, bool *handled);
 

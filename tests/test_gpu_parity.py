@@ -370,10 +370,14 @@ def test_fused_device_tensors_full_size(sep, oracle):
         assert int(res["pit_perm"][b].item()) == int(want["pit"]["idx"][0])
         assert abs(res["pit_loss"][b].item() - want["pit"]["loss"]) < 1e-4 * abs(want["pit"]["loss"])
         assert np.max(np.abs(res["si_pair"][b].cpu().numpy() - want["si_sdr_pair"])) < TOL_DB
-    # host-pointer mode gives the same numbers as device-pointer mode
+    # host-pointer mode gives the same numbers, bit for bit, as device-pointer mode on the same call
+    # (the strip partition -- which frames share a complex transform -- depends on the batch
+    # shape, so the last bit may differ between calls of different batch size)
     host = sep.separate_and_score(mix[:4], masks[:4], refs[:4], **cfg)
-    assert np.array_equal(host["est"], est[:4])
-    assert np.array_equal(host["scores"], res["scores"][:4].cpu().numpy())
+    dev4 = sep.separate_and_score(dm[:4].contiguous(), dk[:4].contiguous(), dr[:4].contiguous(), **cfg)
+    assert np.array_equal(host["est"], dev4["est"].cpu().numpy())
+    assert np.array_equal(host["scores"], dev4["scores"].cpu().numpy())
+    assert rel_err(host["est"], est[:4]) < 1e-6
 
 
 # ----------------------------------------------------------------- a14 conv1d filterbank
