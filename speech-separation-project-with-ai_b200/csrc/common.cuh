@@ -72,6 +72,10 @@ struct sep_plan {
   // pitch of 18 makes a half-warp's paired loads conflict-free)
   float *d_win_t = nullptr;      // 0.5 * analysis
   float *d_syn_t = nullptr;      // synthesis
+  // size 512 only (half-size real transform on the 16x16 core): [16 lanes][18] float2, lane p entry m
+  float2 *d_win2_t = nullptr;    // 0.5 * (w[2p + 32m], w[2p + 32m + 1])
+  float2 *d_syn2_t = nullptr;    // (s[2p + 32m], s[2p + 32m + 1])
+  float2 *d_tw512_t = nullptr;   // exp(-2 pi i (p + 16 m) / 512)
 };
 
 namespace sep {

@@ -328,9 +328,13 @@ extern "C" int sep_fused_separate_ws_f32(const sep_plan *p, const float *mix, co
   a.tw16 = p->d_tw16;
   a.win_t = p->d_win_t;
   a.syn_t = p->d_syn_t;
+  a.win2_t = p->d_win2_t;
+  a.syn2_t = p->d_syn2_t;
+  a.tw512_t = p->d_tw512_t;
 
   bool handled = false;
   if ((rc = fused_strip_try(p, a, batch, C, d_scores, d_sums, s, stream, &handled))) return rc;
+  if (!handled && (rc = fused_strip512_try(p, a, batch, C, d_scores, d_sums, s, stream, &handled))) return rc;
   if (!handled && (rc = fused_fast_try(p, a, batch, C, d_scores, d_sums, s, stream, &handled))) return rc;
   if (!handled) {
     switch (C) {

@@ -25,6 +25,7 @@ struct FusedArgs {
   const float *win_half, *syn;
   const float *win_t, *syn_t;   // [16][18] transposed tables (size 256)
   const float2 *tw_half, *tw_full, *tw16;
+  const float2 *win2_t, *syn2_t, *tw512_t;   // size 512 strip kernel tables, [16][18]
 };
 
 template <int C>
@@ -153,6 +154,8 @@ static int launch_fused_finalize(const FusedArgs &a, int batch, double *d_scores
 // launched; otherwise the generic kernel runs.
 int fused_strip_try(const sep_plan *p, const FusedArgs &a, int batch, int C, double *d_scores,
                     double *d_sums, Scratch &s, cudaStream_t stream, bool *handled);
+int fused_strip512_try(const sep_plan *p, const FusedArgs &a, int batch, int C, double *d_scores,
+                       double *d_sums, Scratch &s, cudaStream_t stream, bool *handled);
 int fused_fast_try(const sep_plan *p, const FusedArgs &a, int batch, int C, double *d_scores,
                    double *d_sums, Scratch &s, cudaStream_t stream, bool *handled);
 

@@ -185,6 +185,22 @@ int sep_plan_create(sep_plan **out, int size, int shift, const double *window, i
       if ((rc = upload(&p->d_win_t, wt)) != SEP_OK) break;
       if ((rc = upload(&p->d_syn_t, st)) != SEP_OK) break;
     }
+    if (size == 512) {
+      std::vector<float2> w2(16 * 18, make_float2(0.f, 0.f)), s2(16 * 18, make_float2(0.f, 0.f)),
+          t2(16 * 18, make_float2(0.f, 0.f));
+      for (int lane = 0; lane < 16; ++lane)
+        for (int m = 0; m < 16; ++m) {
+          const int i0 = 2 * lane + 32 * m;
+          w2[lane * 18 + m] = make_float2(wh[i0], wh[i0 + 1]);
+          s2[lane * 18 + m] = make_float2(ws[i0], ws[i0 + 1]);
+          const int k = lane + 16 * m;
+          t2[lane * 18 + m] = make_float2(static_cast<float>(std::cos(two_pi * k / 512.0)),
+                                          static_cast<float>(-std::sin(two_pi * k / 512.0)));
+        }
+      if ((rc = upload(&p->d_win2_t, w2)) != SEP_OK) break;
+      if ((rc = upload(&p->d_syn2_t, s2)) != SEP_OK) break;
+      if ((rc = upload(&p->d_tw512_t, t2)) != SEP_OK) break;
+    }
   } while (0);
   if (rc != SEP_OK) {
     sep_plan_destroy(p);
@@ -204,6 +220,9 @@ int sep_plan_destroy(sep_plan *p) {
   cudaFree(p->d_tw16);
   cudaFree(p->d_win_t);
   cudaFree(p->d_syn_t);
+  cudaFree(p->d_win2_t);
+  cudaFree(p->d_syn2_t);
+  cudaFree(p->d_tw512_t);
   delete p;
   return SEP_OK;
 }

@@ -337,6 +337,46 @@ def test_fused_matches_oracle(sep, oracle, key, n_src, n):
     assert res["sums"][3] == 3
 
 
+@pytest.mark.parametrize("key,n_src,n,batch", [
+    ("blackman_256_128", 2, 6001, 5),     # odd length: rows not 16-byte aligned -> 4-byte staging, scalar edges
+    ("hann_256_64", 2, 4098, 3),
+    ("hann_256_64", 1, 9000, 2),
+    ("hann_512_128", 3, 7001, 3),
+    ("hann_512_128", 2, 20000, 40),       # many strips per utterance and several strips per warp
+    ("hann_512_128", 1, 3000, 2),
+    ("blackman_256_128", 2, 16000, 70),
+])
+def test_fused_strip_edges(sep, oracle, key, n_src, n, batch):
+    """Strip kernels (size 256 and 512): ragged lengths, valid_samples, est-only mode, strips of
+    unequal length, utterances that end inside a strip -- every utterance against the oracle."""
+    cfg = CONFIGS[key]
+    rng = np.random.default_rng(sum(map(ord, key)) + n_src + n)
+    mix, refs, masks, lengths = _fused_case(rng, batch, n, n_src, cfg, oracle, ragged=True)
+    valid = rng.integers(n // 2, n + 1, size=batch).astype(np.int32)
+    valid[0] = n
+    res = sep.separate_and_score(mix, masks, refs, frame_lengths=lengths, valid_samples=valid, **cfg)
+    only = sep.separate_and_score(mix, masks, None, **cfg)
+    assert np.array_equal(only["est"], res["est"])                # same estimates with and without scoring
+    for b in list(range(min(batch, 3))) + [batch - 1]:
+        want = oracle.separate_and_score(mix[b], refs[b], masks[b], length=lengths[b], **cfg)
+        assert rel_err(res["est"][b], want["ests"][:, :n]) < TOL_REL
+        assert rel_l2(res["est"][b], want["ests"][:, :n]) < 1e-5
+        pit = want["pit"]
+        assert int(res["pit_perm"][b]) == int(pit["idx"][0])
+        assert np.allclose(res["pit_pair"][b], pit["pair"][0], rtol=1e-4)
+        nv = int(valid[b])
+        est32 = want["ests"][:, :nv].astype(np.float32)
+        si = np.array([[oracle.si_sdr(refs[b, j, :nv], est32[i]) for j in range(n_src)] for i in range(n_src)])
+        assert np.max(np.abs(res["si_pair"][b] - si)) < TOL_DB
+    # all-zero mixture frames (digital silence) with non-zero references: label = Re S (angle(0) = 0)
+    mix2 = mix.copy()
+    mix2[:, : n // 3] = 0.0
+    res2 = sep.separate_and_score(mix2, masks, refs, frame_lengths=lengths, **cfg)
+    want2 = oracle.separate_and_score(mix2[0], refs[0], masks[0], length=lengths[0], **cfg)
+    assert np.allclose(res2["pit_pair"][0], want2["pit"]["pair"][0], rtol=1e-4)
+    assert int(res2["pit_perm"][0]) == int(want2["pit"]["idx"][0])
+
+
 def test_fused_est_only_and_identity_mask(sep, oracle):
     """mask == 1 for a single source: est must reproduce the mixture (perfect reconstruction)."""
     rng = np.random.default_rng(1)
