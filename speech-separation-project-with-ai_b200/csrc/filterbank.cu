@@ -24,6 +24,8 @@
 // Operands live in shared memory in the canonical K-major, no-swizzle UMMA layout:
 // 8-row x 16-byte core matrices; LBO = distance between the two 16-byte K chunks of one
 // MMA, SBO = distance between 8-row groups (cute/arch/mma_sm100_desc.hpp).
+#include <cuda.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -34,23 +36,24 @@ constexpr int kFbM = 128;        // frames per tile (MMA M)
 constexpr int kFbN = 256;        // filters
 constexpr int kFbL = 16;         // taps
 constexpr int kFbHop = 8;
-constexpr int kFbChunk = 32;     // code columns per decoder chunk
+constexpr int kFbChunk = 16;     // code columns per decoder work item
+constexpr int kFbWG = 4;         // warpgroups per CTA; warpgroup w takes work items w, w + 4, ...
+constexpr int kFbThreads = 128 * kFbWG;
+constexpr int kFbStages = 2;     // mask tiles in flight per warpgroup (TMA ring, one mbarrier per slot)
 
 // ---- shared memory map (bytes) ----
 constexpr int kA1Bytes = kFbM * kFbL * 4;            // 8 KB   [4 k-chunks][16 row groups][128 B]
 constexpr int kB1Bytes = kFbN * kFbL * 4;            // 16 KB  [4][32][128 B]
 constexpr int kB2Bytes = kFbL * kFbN * 4;            // 16 KB  [64 k-chunks][2][128 B]
-constexpr int kA2Bytes = kFbM * kFbChunk * 4;        // 16 KB  [8 k-chunks][16][128 B]
+constexpr int kA2Bytes = kFbM * kFbChunk * 4;        // 8 KB   [4 k-chunks][16][128 B]
+constexpr int kMaskTile = kFbM * kFbChunk * 4;       // 8 KB   TMA box [128 rows][64 B], SWIZZLE_64B
 constexpr int kOffA1Hi = 0, kOffA1Lo = kOffA1Hi + kA1Bytes;
 constexpr int kOffB1Hi = kOffA1Lo + kA1Bytes, kOffB1Lo = kOffB1Hi + kB1Bytes;
 constexpr int kOffB2Hi = kOffB1Lo + kB1Bytes, kOffB2Lo = kOffB2Hi + kB2Bytes;
-constexpr int kOffA2 = kOffB2Lo + kB2Bytes;          // 2 buffers x (hi, lo)
-constexpr int kOffUp = kOffA2 + 4 * kA2Bytes;        // [128][8] upper frame halves for the overlap-add
-constexpr int kOffBar = kOffUp + kFbM * 8 * 4;       // mbarriers + tmem address
-constexpr int kFbStages = 4;                         // mask tiles in flight (cp.async ring)
-constexpr int kMaskTile = kFbM * kFbChunk * 4;       // 16 KB  [8 float4 columns][128 rows][16 B]
-constexpr int kOffMask = kOffBar + 64;
-constexpr int kFbSmem = kOffMask + kFbStages * kMaskTile;
+constexpr int kOffWG = kOffB2Lo + kB2Bytes;          // per warpgroup: A2 hi, A2 lo, mask ring, `up`
+constexpr int kWGBytes = 2 * kA2Bytes + kFbStages * kMaskTile + kFbM * 8 * 4;
+constexpr int kOffBar = kOffWG + kFbWG * kWGBytes;   // mbarriers + tmem address + has[][] table
+constexpr int kFbSmem = kOffBar + 256;
 
 constexpr uint32_t kLboA1 = 16 * 128, kLboB1 = 32 * 128, kLboB2 = 2 * 128, kLboA2 = 16 * 128, kSbo = 128;
 
@@ -88,6 +91,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "bra.uni WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t}\n"
       :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+// 2-D tiled bulk tensor copy global -> shared, completion on an mbarrier (TMA)
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      :: "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -140,37 +152,61 @@ struct FbArgs {
   int n_src, frames, tiles, batch;
 };
 
-__global__ void __launch_bounds__(128, 1) filterbank_kernel(const FbArgs a) {
-  extern __shared__ __align__(128) unsigned char sm[];
-  const int m = threadIdx.x, warp = m >> 5;
-  const int K = a.frames;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sm + kOffBar);     // [0] gemm1, [1..2] a2 buffers free, [3] d2 ready
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + kOffBar + 32);
-  const uint32_t bar0 = smem_u32(bars), sm0 = smem_u32(sm);
+__device__ __forceinline__ void wg_sync(int wg) {       // named barrier of one warpgroup
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
+}
 
-  if (warp == 0) {
+// One persistent CTA per SM, four warpgroups.  Per tile of 128 frames:
+//   all:        frames -> A1 (warpgroup 0), GEMM 1 into D1 (TMEM columns 0..255)
+//   warpgroup w: work items g = w, w + 4, ... (item = 16 code columns j of source c):
+//               D1 chunk -> registers, relu, times its thread-private staged mask row, split hi/lo
+//               -> the warpgroup's A2 buffer -> its elected thread issues the 6 decoder MMAs into
+//               the warpgroup's own accumulator D2[w][c]; the mask tile of the next item is in flight
+//   epilogue:   warpgroup c sums D2[*][c], overlap-adds neighbouring frames, writes est_c
+// Warpgroups only meet at two block barriers per tile; inside a tile they run on named barriers.
+__global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs a,
+                                                                   const __grid_constant__ CUtensorMap mask_map) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  const int wg = threadIdx.x >> 7, m = threadIdx.x & 127, wq = (threadIdx.x >> 5) & 3;
+  const int K = a.frames, C = a.n_src;
+  // mbarriers: [0] gemm1 done, [1 + w] A2 buffer of warpgroup w free, [1 + kFbWG] all decoder MMAs done
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sm + kOffBar);
+  // [8 + 2 w + s] mask slot s of warpgroup w full (TMA transaction barrier)
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + kOffBar + 192);
+  unsigned char *has = sm + kOffBar + 224;                         // has[w * 4 + c]: warpgroup w feeds source c
+  const uint32_t bar0 = smem_u32(bars), sm0 = smem_u32(sm);
+  unsigned char *wgs = sm + kOffWG + wg * kWGBytes;
+  unsigned char *a2hi = wgs, *a2lo = wgs + kA2Bytes, *ring = wgs + 2 * kA2Bytes;
+  float *up = reinterpret_cast<float *>(wgs + 2 * kA2Bytes + kFbStages * kMaskTile);
+  const int G = (kFbN / kFbChunk) * C;
+
+  if (threadIdx.x < 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
-  if (m == 0) {
-    for (int i = 0; i < 4; ++i) mbar_init(bar0 + 8 * i, 1);
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1);
+    for (int w = 0; w < kFbWG; ++w) mbar_init(bar0 + 8 * (1 + w), 1);
+    mbar_init(bar0 + 8 * (1 + kFbWG), kFbWG);
+    for (int i = 0; i < kFbWG * kFbStages; ++i) mbar_init(bar0 + 8 * (8 + i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int i = 0; i < 16; ++i) has[i] = 0;
+    for (int g = 0; g < G; ++g) has[(g % kFbWG) * 4 + g % C] = 1;
   }
 
-  // ---- operands of GEMM 1 and the decoder weights, split hi / lo, canonical layout ----
-  // (once per CTA: the kernel is persistent over tiles)
+  // ---- operands of GEMM 1 and the decoder weights, split hi / lo, canonical layout (once per CTA) ----
 #pragma unroll 1
-  for (int e0 = 0; e0 < kFbL * kFbN; e0 += 128 * 8) {
-    float we[8], wd[8];
+  for (int e0 = 0; e0 < kFbL * kFbN; e0 += kFbThreads * 4) {
+    float we[4], wd[4];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {                      // all loads first: one L2 latency per 8 elements
-      we[u] = __ldg(a.enc + e0 + 128 * u + m);
-      wd[u] = __ldg(a.dec + e0 + 128 * u + m);
+    for (int u = 0; u < 4; ++u) {
+      we[u] = __ldg(a.enc + e0 + kFbThreads * u + threadIdx.x);
+      wd[u] = __ldg(a.dec + e0 + kFbThreads * u + threadIdx.x);
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < 4; ++u) {
       // enc [L][N] row-major -> B1[n][k = l];  dec [N][L] row-major -> B2[n2 = l][k = n]
-      const int e = e0 + 128 * u + m;
+      const int e = e0 + kFbThreads * u + threadIdx.x;
       const int l = e / kFbN, nn = e % kFbN;
       float hi, lo;
       split_tf32(we[u], hi, lo);
@@ -184,165 +220,215 @@ __global__ void __launch_bounds__(128, 1) filterbank_kernel(const FbArgs a) {
       *reinterpret_cast<float *>(sm + kOffB2Lo + o2) = lo;
     }
   }
-  __syncthreads();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t lane_addr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-  int use[2] = {0, 0};                               // how often each A2 buffer has been filled
-  uint32_t round = 0;                                // tiles done by this CTA (mbarrier phase)
-
-  for (int t = blockIdx.x; t < a.tiles * a.batch; t += gridDim.x, ++round) {
-  const int b = t / a.tiles, tile = t - b * a.tiles;
-  const int k0 = tile * (kFbM - 1);                     // first frame of the tile (1-frame halo)
-  {
-    const int frame = k0 + m;
-    const float *src = a.wave + static_cast<int64_t>(b) * a.n + static_cast<int64_t>(frame) * kFbHop;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {                    // 4 k-chunks of 4 taps
-      float4 hi, lo;
-      float x[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) x[i] = frame < K ? __ldg(src + 4 * q + i) : 0.f;
-      split_tf32(x[0], hi.x, lo.x); split_tf32(x[1], hi.y, lo.y);
-      split_tf32(x[2], hi.z, lo.z); split_tf32(x[3], hi.w, lo.w);
-      const int o = q * (kFbM / 8) * 128 + (m >> 3) * 128 + (m & 7) * 16;
-      *reinterpret_cast<float4 *>(sm + kOffA1Hi + o) = hi;
-      *reinterpret_cast<float4 *>(sm + kOffA1Lo + o) = lo;
-    }
-  }
-  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-
-  // ---- GEMM 1: D1 = A1 * enc, 3xTF32 ----
-  if (m == 0) {
-    constexpr uint32_t idesc = umma_idesc_tf32(kFbM, kFbN);
-    uint32_t acc = 0;
-#pragma unroll
-    for (int pass = 0; pass < 3; ++pass) {           // hi*hi, lo*hi, hi*lo
-      const uint32_t aoff = sm0 + (pass == 1 ? kOffA1Lo : kOffA1Hi);
-      const uint32_t boff = sm0 + (pass == 2 ? kOffB1Lo : kOffB1Hi);
-#pragma unroll
-      for (int ks = 0; ks < kFbL / 8; ++ks) {
-        umma_tf32(tmem, umma_desc(aoff + ks * 2 * kLboA1, kLboA1, kSbo),
-                  umma_desc(boff + ks * 2 * kLboB1, kLboB1, kSbo), idesc, acc);
-        acc = 1;
-      }
-    }
-    umma_commit(bar0);
-  }
-  mbar_wait(bar0, round & 1);
-  tc_fence_after();
-
-  // ---- relu * mask_c -> GEMM 2, 32 code columns at a time, all sources per chunk ----
-  // Work items g = (chunk j, source c).  The 16 KB mask tile of item g is fetched with
-  // cp.async kFbStages - 1 items ahead (each thread stages and later reads only its own
-  // row, so the ring needs no block barrier); the masked code goes to one of two A2
-  // buffers; thread 0 issues the decoder MMAs of item g while everybody prepares g + 1.
-  const int frame = k0 + m;
-  const bool row_ok = frame < K;
-  const bool owner = row_ok && (m > 0 || tile == 0);   // row 0 of a later tile is the halo frame
-  const int C = a.n_src, G = (kFbN / kFbChunk) * C;
-  const float *mbase = a.masks + (static_cast<int64_t>(b) * C * K + (row_ok ? frame : 0)) * kFbN;
-  auto stage_masks = [&](int g) {
-    if (g < G && row_ok) {
-      const int j = g / C, c = g - j * C;
-      const float *src = mbase + static_cast<int64_t>(c) * K * kFbN + j * kFbChunk;
-      unsigned char *dst = sm + kOffMask + (g % kFbStages) * kMaskTile + m * 16;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) cp_async16(dst + q * (kFbM * 16), src + 4 * q);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  for (int g = 0; g < kFbStages - 1; ++g) stage_masks(g);
-  float d[32];
-  for (int g = 0; g < G; ++g) {
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16);
+  uint32_t use = 0;                                    // how often this warpgroup's A2 buffer has been filled
+  uint32_t fills = 0;                                  // mask tiles this warpgroup has consumed (slot + phase)
+  const uint32_t ring_u32 = smem_u32(ring), full0 = bar0 + 8 * (8 + kFbStages * wg);
+  // TMA of the mask tile of work item g of tile (b, k0) into ring slot `slot` (issued by one thread)
+  auto issue_masks = [&](int b, int k0, int g, uint32_t slot) {
     const int j = g / C, c = g - j * C;
-    if (c == 0) {
-      tmem_ld32(lane_addr + j * kFbChunk, d);
+    mbar_expect_tx(full0 + 8 * slot, kMaskTile);
+    tma_load_2d(ring_u32 + slot * kMaskTile, &mask_map, j * kFbChunk, (b * C + c) * K + k0, full0 + 8 * slot);
+  };
+  if (m == 0 && blockIdx.x < a.tiles * a.batch) {
+    const int b = blockIdx.x / a.tiles, tile = blockIdx.x - b * a.tiles;
+    issue_masks(b, tile * (kFbM - 1), wg, 0);
+  }
+  uint32_t round = 0;                                  // tiles done by this CTA (mbarrier phase)
+
+  for (int t = blockIdx.x; t < a.tiles * a.batch; t += gridDim.x, ++round) {
+    const int b = t / a.tiles, tile = t - b * a.tiles;
+    const int k0 = tile * (kFbM - 1);                     // first frame of the tile (1-frame halo)
+    const int frame = k0 + m;
+    const bool row_ok = frame < K;
+    const bool owner = row_ok && (m > 0 || tile == 0);    // row 0 of a later tile is the halo frame
+    if (wg == 0) {
+      const float *src = a.wave + static_cast<int64_t>(b) * a.n + static_cast<int64_t>(frame) * kFbHop;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) d[i] = fmaxf(d[i], 0.f);
-      if (a.code && owner) {
+      for (int q = 0; q < 4; ++q) {                    // 4 k-chunks of 4 taps
+        float4 x = row_ok ? __ldg(reinterpret_cast<const float4 *>(src) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 hi, lo;
+        split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y);
+        split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
+        const int o = q * (kFbM / 8) * 128 + (m >> 3) * 128 + (m & 7) * 16;
+        *reinterpret_cast<float4 *>(sm + kOffA1Hi + o) = hi;
+        *reinterpret_cast<float4 *>(sm + kOffA1Lo + o) = lo;
+      }
+      fence_async_smem();
+    }
+    tc_fence_before();
+    __syncthreads();                                     // A1 ready; every read of D1 / D2 / `up` of the last tile is done
+    tc_fence_after();
+
+    // ---- GEMM 1: D1 = A1 * enc, 3xTF32 ----
+    if (threadIdx.x == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(kFbM, kFbN);
+      uint32_t acc = 0;
+#pragma unroll
+      for (int pass = 0; pass < 3; ++pass) {           // hi*hi, lo*hi, hi*lo
+        const uint32_t aoff = sm0 + (pass == 1 ? kOffA1Lo : kOffA1Hi);
+        const uint32_t boff = sm0 + (pass == 2 ? kOffB1Lo : kOffB1Hi);
+#pragma unroll
+        for (int ks = 0; ks < kFbL / 8; ++ks) {
+          umma_tf32(tmem, umma_desc(aoff + ks * 2 * kLboA1, kLboA1, kSbo),
+                    umma_desc(boff + ks * 2 * kLboB1, kLboB1, kSbo), idesc, acc);
+          acc = 1;
+        }
+      }
+      umma_commit(bar0);
+    }
+    mbar_wait(bar0, round & 1);
+    tc_fence_after();
+
+    // ---- this warpgroup's work items ----
+    uint32_t touched = 0;                               // sources whose accumulator D2[wg][c] has been started
+    int i = 0;
+    for (int g = wg; g < G; g += kFbWG, ++i) {
+      const int j = g / C, c = g - j * C;
+      float d[kFbChunk];
+      tmem_ld16(lane_addr + j * kFbChunk, d);
+#pragma unroll
+      for (int e = 0; e < kFbChunk; ++e) d[e] = fmaxf(d[e], 0.f);
+      if (a.code && owner && c == 0) {
         float4 *dst = reinterpret_cast<float4 *>(a.code + (static_cast<int64_t>(b) * K + frame) * kFbN + j * kFbChunk);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) dst[q] = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
+        for (int q = 0; q < kFbChunk / 4; ++q) dst[q] = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
       }
-    }
-    stage_masks(g + kFbStages - 1);
-    asm volatile("cp.async.wait_group %0;" :: "n"(kFbStages - 1) : "memory");
-    const int buf = g & 1;
-    if (use[buf] > 0) mbar_wait(bar0 + 8 * (1 + buf), (use[buf] - 1) & 1);   // MMAs that read it are done
-    unsigned char *a2hi = sm + kOffA2 + buf * 2 * kA2Bytes, *a2lo = a2hi + kA2Bytes;
-    const unsigned char *mk_s = sm + kOffMask + (g % kFbStages) * kMaskTile + m * 16;
+      // next item's mask tile (of this tile, or the first item of this CTA's next tile) into the other
+      // slot: every thread of the warpgroup passed the named barrier of the item that last read it
+      const uint32_t slot = fills % kFbStages;
+      if (m == 0) {
+        if (g + kFbWG < G) issue_masks(b, k0, g + kFbWG, (fills + 1) % kFbStages);
+        else if (t + static_cast<int>(gridDim.x) < a.tiles * a.batch) {
+          const int tn = t + gridDim.x, bn = tn / a.tiles;
+          issue_masks(bn, (tn - bn * a.tiles) * (kFbM - 1), wg, (fills + 1) % kFbStages);
+        }
+      }
+      mbar_wait(full0 + 8 * slot, (fills / kFbStages) & 1);
+      ++fills;
+      if (use > 0) mbar_wait(bar0 + 8 * (1 + wg), (use - 1) & 1);   // the MMAs that read the A2 buffer are done
+      // SWIZZLE_64B: 16-byte chunk q of row m sits at chunk q ^ ((m >> 1) & 3)
+      const unsigned char *mk_s = ring + slot * kMaskTile + m * 64;
+      const int sw = (m >> 1) & 3;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 mk = row_ok ? *reinterpret_cast<const float4 *>(mk_s + q * (kFbM * 16))
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 hi, lo;
-      split_tf32(d[4 * q] * mk.x, hi.x, lo.x); split_tf32(d[4 * q + 1] * mk.y, hi.y, lo.y);
-      split_tf32(d[4 * q + 2] * mk.z, hi.z, lo.z); split_tf32(d[4 * q + 3] * mk.w, hi.w, lo.w);
-      const int o = q * (kFbM / 8) * 128 + (m >> 3) * 128 + (m & 7) * 16;
-      *reinterpret_cast<float4 *>(a2hi + o) = hi;
-      *reinterpret_cast<float4 *>(a2lo + o) = lo;
+      for (int q = 0; q < kFbChunk / 4; ++q) {
+        const float4 mk = row_ok ? *reinterpret_cast<const float4 *>(mk_s + ((q ^ sw) << 4))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 hi, lo;
+        split_tf32(d[4 * q] * mk.x, hi.x, lo.x); split_tf32(d[4 * q + 1] * mk.y, hi.y, lo.y);
+        split_tf32(d[4 * q + 2] * mk.z, hi.z, lo.z); split_tf32(d[4 * q + 3] * mk.w, hi.w, lo.w);
+        const int o = q * (kFbM / 8) * 128 + (m >> 3) * 128 + (m & 7) * 16;
+        *reinterpret_cast<float4 *>(a2hi + o) = hi;
+        *reinterpret_cast<float4 *>(a2lo + o) = lo;
+      }
+      ++use;
+      fence_async_smem();
+      tc_fence_before();
+      wg_sync(wg);
+      tc_fence_after();
+      if (m == 0) {
+        constexpr uint32_t idesc = umma_idesc_tf32(kFbM, kFbL);
+        const uint32_t a2 = smem_u32(a2hi);
+        const uint32_t dcol = tmem + kFbN + kFbL * (wg * C + c);
+        uint32_t acc = (touched >> c) & 1u;
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t aoff = a2 + (pass == 1 ? kA2Bytes : 0);
+          const uint32_t boff = sm0 + (pass == 2 ? kOffB2Lo : kOffB2Hi) + j * (kFbChunk / 4) * kLboB2;
+#pragma unroll
+          for (int ks = 0; ks < kFbChunk / 8; ++ks) {
+            umma_tf32(dcol, umma_desc(aoff + ks * 2 * kLboA2, kLboA2, kSbo),
+                      umma_desc(boff + ks * 2 * kLboB2, kLboB2, kSbo), idesc, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(bar0 + 8 * (1 + wg));
+      }
+      touched |= 1u << c;
     }
-    ++use[buf];
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
+    if (m == 0) umma_commit(bar0 + 8 * (1 + kFbWG));      // this warpgroup's decoder MMAs, all of them
+    mbar_wait(bar0 + 8 * (1 + kFbWG), round & 1);
     tc_fence_after();
-    if (m == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(kFbM, kFbL);
-      const uint32_t a2 = sm0 + kOffA2 + buf * 2 * kA2Bytes;
-#pragma unroll
-      for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t aoff = a2 + (pass == 1 ? kA2Bytes : 0);
-        const uint32_t boff = sm0 + (pass == 2 ? kOffB2Lo : kOffB2Hi) + j * (kFbChunk / 4) * kLboB2;
-#pragma unroll
-        for (int ks = 0; ks < kFbChunk / 8; ++ks)
-          umma_tf32(tmem + kFbN + kFbL * c, umma_desc(aoff + ks * 2 * kLboA2, kLboA2, kSbo),
-                    umma_desc(boff + ks * 2 * kLboB2, kLboB2, kSbo), idesc, (j | pass | ks) != 0 ? 1u : 0u);
-      }
-      umma_commit(bar0 + 8 * (1 + buf));
-      if (g == G - 1) umma_commit(bar0 + 8 * 3);
-    }
-  }
-  mbar_wait(bar0 + 8 * 3, round & 1);
-  tc_fence_after();
 
-  // ---- D2_c -> registers -> overlap-add of neighbouring frames -> est ----
-  for (int c = 0; c < C; ++c) {
-    float y[16];
-    tmem_ld16(lane_addr + kFbN + kFbL * c, y);
-    // hop-block h = frame gets y[frame][0:8] + y[frame-1][8:16]
-    float *up = reinterpret_cast<float *>(sm + kOffUp);
+    // ---- sum of the warpgroups' D2_c -> overlap-add of neighbouring frames -> est ----
+    for (int c = wg; c < C; c += kFbWG) {
+      float y[16];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) up[m * 8 + i] = y[8 + i];
-    __syncthreads();
-    float *out = a.est + (static_cast<int64_t>(b) * C + c) * a.est_len;
-    if (owner) {
-      float4 lo4 = make_float4(y[0], y[1], y[2], y[3]), hi4 = make_float4(y[4], y[5], y[6], y[7]);
-      if (m > 0) {
-        const float *p = up + (m - 1) * 8;
-        lo4.x += p[0]; lo4.y += p[1]; lo4.z += p[2]; lo4.w += p[3];
-        hi4.x += p[4]; hi4.y += p[5]; hi4.z += p[6]; hi4.w += p[7];
+      for (int e = 0; e < 16; ++e) y[e] = 0.f;
+      for (int w = 0; w < kFbWG; ++w) {
+        if (!has[w * 4 + c]) continue;
+        float p[16];
+        tmem_ld16(lane_addr + kFbN + kFbL * (w * C + c), p);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) y[e] += p[e];
       }
-      float4 *dst = reinterpret_cast<float4 *>(out + static_cast<int64_t>(frame) * kFbHop);
-      dst[0] = lo4;
-      dst[1] = hi4;
-      if (frame == K - 1) {                              // the tail hop-block of the utterance
-        dst[2] = make_float4(y[8], y[9], y[10], y[11]);
-        dst[3] = make_float4(y[12], y[13], y[14], y[15]);
+      // hop-block h = frame gets y[frame][0:8] + y[frame-1][8:16]
+#pragma unroll
+      for (int e = 0; e < 8; ++e) up[m * 8 + e] = y[8 + e];
+      wg_sync(wg);
+      float *out = a.est + (static_cast<int64_t>(b) * C + c) * a.est_len;
+      if (owner) {
+        float4 lo4 = make_float4(y[0], y[1], y[2], y[3]), hi4 = make_float4(y[4], y[5], y[6], y[7]);
+        if (m > 0) {
+          const float *p = up + (m - 1) * 8;
+          lo4.x += p[0]; lo4.y += p[1]; lo4.z += p[2]; lo4.w += p[3];
+          hi4.x += p[4]; hi4.y += p[5]; hi4.z += p[6]; hi4.w += p[7];
+        }
+        float4 *dst = reinterpret_cast<float4 *>(out + static_cast<int64_t>(frame) * kFbHop);
+        dst[0] = lo4;
+        dst[1] = hi4;
+        if (frame == K - 1) {                              // the tail hop-block of the utterance
+          dst[2] = make_float4(y[8], y[9], y[10], y[11]);
+          dst[3] = make_float4(y[12], y[13], y[14], y[15]);
+        }
       }
+      wg_sync(wg);                                        // `up` is reused by this warpgroup's next source
     }
-    __syncthreads();                                    // `up` is reused by the next source
-  }
-  tc_fence_before();                                    // D1 / D2 are overwritten by the next tile
+    tc_fence_before();                                    // D1 / D2 are overwritten by the next tile
   }  // tile loop
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0)
+  if (threadIdx.x < 32)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u));
+}
+
+// Tensor map of the masks seen as [rows = B * C * K][256] float32, box [128 rows][16 columns],
+// SWIZZLE_64B.  The driver entry point is resolved at run time (no link against libcuda).
+static int make_mask_map(CUtensorMap *map, const float *masks, uint64_t rows) {
+  typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    SEP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !fn) {
+      set_error("cuTensorMapEncodeTiled is not available from this driver");
+      return SEP_ERR_CUDA;
+    }
+    encode = reinterpret_cast<encode_fn>(fn);
+  }
+  if (reinterpret_cast<uintptr_t>(masks) & 15) {
+    set_error("sep_filterbank_separate_f32: masks must be 16-byte aligned");
+    return SEP_ERR_INVALID;
+  }
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kFbN), rows};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kFbN) * 4};
+  const cuuint32_t box[2] = {kFbChunk, kFbM}, elem[2] = {1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(masks), dims, strides, box,
+                            elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+    return SEP_ERR_CUDA;
+  }
+  return SEP_OK;
 }
 
 }  // namespace sep
@@ -390,8 +476,10 @@ extern "C" int sep_filterbank_separate_f32(const float *wave, const float *enc, 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   // persistent: one CTA per SM (its 200+ KB of shared memory and 512 TMEM columns fill the SM)
   dim3 grid(static_cast<unsigned>(std::min<int64_t>(static_cast<int64_t>(a.tiles) * batch, sms)));
+  CUtensorMap mask_map;
+  if ((rc = make_mask_map(&mask_map, a.masks, static_cast<uint64_t>(batch) * n_src * K))) return rc;
   profile_begin(stream);
-  filterbank_kernel<<<grid, 128, kFbSmem, stream>>>(a);
+  filterbank_kernel<<<grid, kFbThreads, kFbSmem, stream>>>(a, mask_map);
   profile_end(stream);
   SEP_LAUNCHED();
   if ((rc = copy_back(s, est, a.est, n_est, mem))) return rc;
