@@ -27,6 +27,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -38,7 +39,7 @@ constexpr int kFbL = 16;         // taps
 constexpr int kFbHop = 8;
 constexpr int kFbChunk = 16;     // code columns per decoder work item
 constexpr int kFbWG = 4;         // warpgroups per CTA; warpgroup w takes work items w, w + 4, ...
-constexpr int kFbThreads = 128 * kFbWG;
+constexpr int kFbThreads = 128 * kFbWG + 64;   // + one MMA-issue warp + one TMA / frame-staging warp
 constexpr int kFbStages = 2;     // mask tiles in flight per warpgroup (TMA ring, one mbarrier per slot)
 
 // ---- shared memory map (bytes) ----
@@ -53,7 +54,7 @@ constexpr int kOffB2Hi = kOffB1Lo + kB1Bytes, kOffB2Lo = kOffB2Hi + kB2Bytes;
 constexpr int kOffWG = kOffB2Lo + kB2Bytes;          // per warpgroup: A2 hi, A2 lo, mask ring, `up`
 constexpr int kWGBytes = 2 * kA2Bytes + kFbStages * kMaskTile + kFbM * 8 * 4;
 constexpr int kOffBar = kOffWG + kFbWG * kWGBytes;   // mbarriers + tmem address + has[][] table
-constexpr int kFbSmem = kOffBar + 256;
+constexpr int kFbSmem = kOffBar + 512;
 
 constexpr uint32_t kLboA1 = 16 * 128, kLboB1 = 32 * 128, kLboB2 = 2 * 128, kLboA2 = 16 * 128, kSbo = 128;
 
@@ -87,10 +88,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n\t.reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra.uni WAIT_DONE;\n\t"
-      "bra.uni WAIT_LOOP;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t}\n"
       :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
@@ -156,240 +166,330 @@ __device__ __forceinline__ void wg_sync(int wg) {       // named barrier of one 
   asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
 }
 
-// One persistent CTA per SM, four warpgroups.  Per tile of 128 frames:
-//   all:        frames -> A1 (warpgroup 0), GEMM 1 into D1 (TMEM columns 0..255)
-//   warpgroup w: work items g = w, w + 4, ... (item = 16 code columns j of source c):
-//               D1 chunk -> registers, relu, times its thread-private staged mask row, split hi/lo
-//               -> the warpgroup's A2 buffer -> its elected thread issues the 6 decoder MMAs into
-//               the warpgroup's own accumulator D2[w][c]; the mask tile of the next item is in flight
-//   epilogue:   warpgroup c sums D2[*][c], overlap-adds neighbouring frames, writes est_c
-// Warpgroups only meet at two block barriers per tile; inside a tile they run on named barriers.
+// One persistent CTA per SM, warp-specialised:
+//   warpgroups 0..3 (consumers): per work item (16 code columns j of source c) of a 128-frame tile:
+//       D1 chunk -> registers (tcgen05.ld), relu, times the mask tile in shared memory, split hi / lo
+//       -> the warpgroup's A2 buffer -> arrive on `a2_ready`; then the epilogue of the tile
+//   warp 16 (MMA): GEMM 1 of every tile as soon as its frames are staged and D1 has been drained;
+//       the 6 decoder MMAs of whichever warpgroup's A2 buffer is ready, into that warpgroup's own
+//       accumulator D2[w][c]; commits free the A2 buffers / publish D1 and D2
+//   warp 17 (producer): mask tiles by TMA into per-warpgroup rings, the next tile's frames -> A1
+// Nobody meets at a block barrier inside the tile loop; all hand-offs are mbarriers.
+enum : int {
+  kBarG1 = 0,            // GEMM 1 of the tile done (commit)
+  kBarD2 = 1,            // all decoder MMAs of the tile done (commit)
+  kBarA1 = 2,            // frames of the tile staged (32 producer lanes)
+  kBarD1Free = 3,        // every consumer has read its last D1 chunk (512)
+  kBarD2Free = 4,        // the epilogue has read D2 (128 per source)
+  kBarA2Ready = 8,       // [w] masked code of an item written (128)
+  kBarA2Free = 12,       // [w] decoder MMAs of that item done (commit)
+  kBarFull = 16,         // [w * stages + s] mask tile landed (TMA transaction)
+  kBarEmpty = 24,        // [w * stages + s] mask tile read by the whole warpgroup (128)
+};
+
 __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs a,
                                                                    const __grid_constant__ CUtensorMap mask_map) {
   extern __shared__ __align__(128) unsigned char sm[];
-  const int wg = threadIdx.x >> 7, m = threadIdx.x & 127, wq = (threadIdx.x >> 5) & 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wg = threadIdx.x >> 7, m = threadIdx.x & 127, wq = warp & 3;
   const int K = a.frames, C = a.n_src;
-  // mbarriers: [0] gemm1 done, [1 + w] A2 buffer of warpgroup w free, [1 + kFbWG] all decoder MMAs done
   uint64_t *bars = reinterpret_cast<uint64_t *>(sm + kOffBar);
-  // [8 + 2 w + s] mask slot s of warpgroup w full (TMA transaction barrier)
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + kOffBar + 192);
-  unsigned char *has = sm + kOffBar + 224;                         // has[w * 4 + c]: warpgroup w feeds source c
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + kOffBar + 384);
+  unsigned char *has = sm + kOffBar + 400;                         // has[w * 4 + c]: warpgroup w feeds source c
   const uint32_t bar0 = smem_u32(bars), sm0 = smem_u32(sm);
-  unsigned char *wgs = sm + kOffWG + wg * kWGBytes;
-  unsigned char *a2hi = wgs, *a2lo = wgs + kA2Bytes, *ring = wgs + 2 * kA2Bytes;
-  float *up = reinterpret_cast<float *>(wgs + 2 * kA2Bytes + kFbStages * kMaskTile);
+#define SEP_BAR(i) (bar0 + 8u * static_cast<uint32_t>(i))
   const int G = (kFbN / kFbChunk) * C;
+  const int n_tiles = a.tiles * a.batch;
 
   if (threadIdx.x < 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   if (threadIdx.x == 0) {
-    mbar_init(bar0, 1);
-    for (int w = 0; w < kFbWG; ++w) mbar_init(bar0 + 8 * (1 + w), 1);
-    mbar_init(bar0 + 8 * (1 + kFbWG), kFbWG);
-    for (int i = 0; i < kFbWG * kFbStages; ++i) mbar_init(bar0 + 8 * (8 + i), 1);
+    mbar_init(SEP_BAR(kBarG1), 1);
+    mbar_init(SEP_BAR(kBarD2), 1);
+    mbar_init(SEP_BAR(kBarA1), 32);
+    mbar_init(SEP_BAR(kBarD1Free), 128 * kFbWG);
+    mbar_init(SEP_BAR(kBarD2Free), 128 * (C < kFbWG ? C : kFbWG));
+    for (int w = 0; w < kFbWG; ++w) {
+      mbar_init(SEP_BAR(kBarA2Ready + w), 128);
+      mbar_init(SEP_BAR(kBarA2Free + w), 1);
+      for (int st = 0; st < kFbStages; ++st) {
+        mbar_init(SEP_BAR(kBarFull + w * kFbStages + st), 1);
+        mbar_init(SEP_BAR(kBarEmpty + w * kFbStages + st), 128);
+      }
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int i = 0; i < 16; ++i) has[i] = 0;
     for (int g = 0; g < G; ++g) has[(g % kFbWG) * 4 + g % C] = 1;
   }
 
-  // ---- operands of GEMM 1 and the decoder weights, split hi / lo, canonical layout (once per CTA) ----
+  // ---- encoder and decoder weights, split hi / lo, canonical layout (once per CTA) ----
 #pragma unroll 1
-  for (int e0 = 0; e0 < kFbL * kFbN; e0 += kFbThreads * 4) {
-    float we[4], wd[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      we[u] = __ldg(a.enc + e0 + kFbThreads * u + threadIdx.x);
-      wd[u] = __ldg(a.dec + e0 + kFbThreads * u + threadIdx.x);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      // enc [L][N] row-major -> B1[n][k = l];  dec [N][L] row-major -> B2[n2 = l][k = n]
-      const int e = e0 + kFbThreads * u + threadIdx.x;
-      const int l = e / kFbN, nn = e % kFbN;
-      float hi, lo;
-      split_tf32(we[u], hi, lo);
-      const int o1 = kmajor_off(nn, l, kFbN / 8);
-      *reinterpret_cast<float *>(sm + kOffB1Hi + o1) = hi;
-      *reinterpret_cast<float *>(sm + kOffB1Lo + o1) = lo;
-      const int nf = e / kFbL, ll = e % kFbL;
-      split_tf32(wd[u], hi, lo);
-      const int o2 = kmajor_off(ll, nf, kFbL / 8);
-      *reinterpret_cast<float *>(sm + kOffB2Hi + o2) = hi;
-      *reinterpret_cast<float *>(sm + kOffB2Lo + o2) = lo;
-    }
+  for (int e = threadIdx.x; e < kFbL * kFbN; e += kFbThreads) {
+    // enc [L][N] row-major -> B1[n][k = l];  dec [N][L] row-major -> B2[n2 = l][k = n]
+    const int l = e / kFbN, nn = e % kFbN;
+    float hi, lo;
+    split_tf32(__ldg(a.enc + e), hi, lo);
+    const int o1 = kmajor_off(nn, l, kFbN / 8);
+    *reinterpret_cast<float *>(sm + kOffB1Hi + o1) = hi;
+    *reinterpret_cast<float *>(sm + kOffB1Lo + o1) = lo;
+    const int nf = e / kFbL, ll = e % kFbL;
+    split_tf32(__ldg(a.dec + e), hi, lo);
+    const int o2 = kmajor_off(ll, nf, kFbL / 8);
+    *reinterpret_cast<float *>(sm + kOffB2Hi + o2) = hi;
+    *reinterpret_cast<float *>(sm + kOffB2Lo + o2) = lo;
   }
+  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16);
-  uint32_t use = 0;                                    // how often this warpgroup's A2 buffer has been filled
-  uint32_t fills = 0;                                  // mask tiles this warpgroup has consumed (slot + phase)
-  const uint32_t ring_u32 = smem_u32(ring), full0 = bar0 + 8 * (8 + kFbStages * wg);
-  // TMA of the mask tile of work item g of tile (b, k0) into ring slot `slot` (issued by one thread)
-  auto issue_masks = [&](int b, int k0, int g, uint32_t slot) {
-    const int j = g / C, c = g - j * C;
-    mbar_expect_tx(full0 + 8 * slot, kMaskTile);
-    tma_load_2d(ring_u32 + slot * kMaskTile, &mask_map, j * kFbChunk, (b * C + c) * K + k0, full0 + 8 * slot);
-  };
-  if (m == 0 && blockIdx.x < a.tiles * a.batch) {
-    const int b = blockIdx.x / a.tiles, tile = blockIdx.x - b * a.tiles;
-    issue_masks(b, tile * (kFbM - 1), wg, 0);
-  }
-  uint32_t round = 0;                                  // tiles done by this CTA (mbarrier phase)
 
-  for (int t = blockIdx.x; t < a.tiles * a.batch; t += gridDim.x, ++round) {
-    const int b = t / a.tiles, tile = t - b * a.tiles;
-    const int k0 = tile * (kFbM - 1);                     // first frame of the tile (1-frame halo)
-    const int frame = k0 + m;
-    const bool row_ok = frame < K;
-    const bool owner = row_ok && (m > 0 || tile == 0);    // row 0 of a later tile is the halo frame
-    if (wg == 0) {
-      const float *src = a.wave + static_cast<int64_t>(b) * a.n + static_cast<int64_t>(frame) * kFbHop;
+  if (warp == 4 * kFbWG) {
+    // =========================== MMA warp (one lane issues) ===========================
+    if (lane == 0) {
+      uint32_t served[kFbWG];                          // items served per warpgroup, all tiles (phase of a2_ready)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {                    // 4 k-chunks of 4 taps
-        float4 x = row_ok ? __ldg(reinterpret_cast<const float4 *>(src) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 hi, lo;
-        split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y);
-        split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
-        const int o = q * (kFbM / 8) * 128 + (m >> 3) * 128 + (m & 7) * 16;
-        *reinterpret_cast<float4 *>(sm + kOffA1Hi + o) = hi;
-        *reinterpret_cast<float4 *>(sm + kOffA1Lo + o) = lo;
-      }
-      fence_async_smem();
-    }
-    tc_fence_before();
-    __syncthreads();                                     // A1 ready; every read of D1 / D2 / `up` of the last tile is done
-    tc_fence_after();
-
-    // ---- GEMM 1: D1 = A1 * enc, 3xTF32 ----
-    if (threadIdx.x == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(kFbM, kFbN);
-      uint32_t acc = 0;
+      for (int w = 0; w < kFbWG; ++w) served[w] = 0;
+      uint32_t round = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++round) {
+        mbar_wait(SEP_BAR(kBarA1), round & 1);                             // frames staged
+        if (round > 0) mbar_wait(SEP_BAR(kBarD1Free), (round - 1) & 1);      // D1 of the last tile drained
+        tc_fence_after();
+        {
+          constexpr uint32_t idesc = umma_idesc_tf32(kFbM, kFbN);
+          uint32_t acc = 0;
 #pragma unroll
-      for (int pass = 0; pass < 3; ++pass) {           // hi*hi, lo*hi, hi*lo
-        const uint32_t aoff = sm0 + (pass == 1 ? kOffA1Lo : kOffA1Hi);
-        const uint32_t boff = sm0 + (pass == 2 ? kOffB1Lo : kOffB1Hi);
+          for (int pass = 0; pass < 3; ++pass) {         // hi*hi, lo*hi, hi*lo
+            const uint32_t aoff = sm0 + (pass == 1 ? kOffA1Lo : kOffA1Hi);
+            const uint32_t boff = sm0 + (pass == 2 ? kOffB1Lo : kOffB1Hi);
 #pragma unroll
-        for (int ks = 0; ks < kFbL / 8; ++ks) {
-          umma_tf32(tmem, umma_desc(aoff + ks * 2 * kLboA1, kLboA1, kSbo),
-                    umma_desc(boff + ks * 2 * kLboB1, kLboB1, kSbo), idesc, acc);
-          acc = 1;
+            for (int ks = 0; ks < kFbL / 8; ++ks) {
+              umma_tf32(tmem, umma_desc(aoff + ks * 2 * kLboA1, kLboA1, kSbo),
+                        umma_desc(boff + ks * 2 * kLboB1, kLboB1, kSbo), idesc, acc);
+              acc = 1;
+            }
+          }
+          umma_commit(SEP_BAR(kBarG1));
         }
-      }
-      umma_commit(bar0);
-    }
-    mbar_wait(bar0, round & 1);
-    tc_fence_after();
-
-    // ---- this warpgroup's work items ----
-    uint32_t touched = 0;                               // sources whose accumulator D2[wg][c] has been started
-    int i = 0;
-    for (int g = wg; g < G; g += kFbWG, ++i) {
-      const int j = g / C, c = g - j * C;
-      float d[kFbChunk];
-      tmem_ld16(lane_addr + j * kFbChunk, d);
-#pragma unroll
-      for (int e = 0; e < kFbChunk; ++e) d[e] = fmaxf(d[e], 0.f);
-      if (a.code && owner && c == 0) {
-        float4 *dst = reinterpret_cast<float4 *>(a.code + (static_cast<int64_t>(b) * K + frame) * kFbN + j * kFbChunk);
-#pragma unroll
-        for (int q = 0; q < kFbChunk / 4; ++q) dst[q] = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
-      }
-      // next item's mask tile (of this tile, or the first item of this CTA's next tile) into the other
-      // slot: every thread of the warpgroup passed the named barrier of the item that last read it
-      const uint32_t slot = fills % kFbStages;
-      if (m == 0) {
-        if (g + kFbWG < G) issue_masks(b, k0, g + kFbWG, (fills + 1) % kFbStages);
-        else if (t + static_cast<int>(gridDim.x) < a.tiles * a.batch) {
-          const int tn = t + gridDim.x, bn = tn / a.tiles;
-          issue_masks(bn, (tn - bn * a.tiles) * (kFbM - 1), wg, (fills + 1) % kFbStages);
+        if (round > 0) {                                 // D2 of the last tile read by its epilogue
+          mbar_wait(SEP_BAR(kBarD2Free), (round - 1) & 1);
+          tc_fence_after();
         }
-      }
-      mbar_wait(full0 + 8 * slot, (fills / kFbStages) & 1);
-      ++fills;
-      if (use > 0) mbar_wait(bar0 + 8 * (1 + wg), (use - 1) & 1);   // the MMAs that read the A2 buffer are done
-      // SWIZZLE_64B: 16-byte chunk q of row m sits at chunk q ^ ((m >> 1) & 3)
-      const unsigned char *mk_s = ring + slot * kMaskTile + m * 64;
-      const int sw = (m >> 1) & 3;
+        uint32_t next[kFbWG], touched[kFbWG];
 #pragma unroll
-      for (int q = 0; q < kFbChunk / 4; ++q) {
-        const float4 mk = row_ok ? *reinterpret_cast<const float4 *>(mk_s + ((q ^ sw) << 4))
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 hi, lo;
-        split_tf32(d[4 * q] * mk.x, hi.x, lo.x); split_tf32(d[4 * q + 1] * mk.y, hi.y, lo.y);
-        split_tf32(d[4 * q + 2] * mk.z, hi.z, lo.z); split_tf32(d[4 * q + 3] * mk.w, hi.w, lo.w);
-        const int o = q * (kFbM / 8) * 128 + (m >> 3) * 128 + (m & 7) * 16;
-        *reinterpret_cast<float4 *>(a2hi + o) = hi;
-        *reinterpret_cast<float4 *>(a2lo + o) = lo;
-      }
-      ++use;
-      fence_async_smem();
-      tc_fence_before();
-      wg_sync(wg);
-      tc_fence_after();
-      if (m == 0) {
-        constexpr uint32_t idesc = umma_idesc_tf32(kFbM, kFbL);
-        const uint32_t a2 = smem_u32(a2hi);
-        const uint32_t dcol = tmem + kFbN + kFbL * (wg * C + c);
-        uint32_t acc = (touched >> c) & 1u;
+        for (int w = 0; w < kFbWG; ++w) { next[w] = 0; touched[w] = 0; }
+        int left = G;
+        while (left > 0) {
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t aoff = a2 + (pass == 1 ? kA2Bytes : 0);
-          const uint32_t boff = sm0 + (pass == 2 ? kOffB2Lo : kOffB2Hi) + j * (kFbChunk / 4) * kLboB2;
+          for (int w = 0; w < kFbWG; ++w) {
+            const int g = w + static_cast<int>(next[w]) * kFbWG;
+            if (g >= G || !mbar_try(SEP_BAR(kBarA2Ready + w), served[w] & 1)) continue;
+            tc_fence_after();
+            const int j = g / C, c = g - j * C;
+            constexpr uint32_t idesc = umma_idesc_tf32(kFbM, kFbL);
+            const uint32_t a2 = sm0 + kOffWG + w * kWGBytes;
+            const uint32_t dcol = tmem + kFbN + kFbL * (w * C + c);
+            uint32_t acc = (touched[w] >> c) & 1u;
 #pragma unroll
-          for (int ks = 0; ks < kFbChunk / 8; ++ks) {
-            umma_tf32(dcol, umma_desc(aoff + ks * 2 * kLboA2, kLboA2, kSbo),
-                      umma_desc(boff + ks * 2 * kLboB2, kLboB2, kSbo), idesc, acc);
-            acc = 1;
+            for (int pass = 0; pass < 3; ++pass) {
+              const uint32_t aoff = a2 + (pass == 1 ? kA2Bytes : 0);
+              const uint32_t boff = sm0 + (pass == 2 ? kOffB2Lo : kOffB2Hi) + j * (kFbChunk / 4) * kLboB2;
+#pragma unroll
+              for (int ks = 0; ks < kFbChunk / 8; ++ks) {
+                umma_tf32(dcol, umma_desc(aoff + ks * 2 * kLboA2, kLboA2, kSbo),
+                          umma_desc(boff + ks * 2 * kLboB2, kLboB2, kSbo), idesc, acc);
+                acc = 1;
+              }
+            }
+            umma_commit(SEP_BAR(kBarA2Free + w));
+            touched[w] |= 1u << c;
+            ++next[w];
+            ++served[w];
+            --left;
           }
         }
-        umma_commit(bar0 + 8 * (1 + wg));
+        umma_commit(SEP_BAR(kBarD2));
       }
-      touched |= 1u << c;
     }
-    if (m == 0) umma_commit(bar0 + 8 * (1 + kFbWG));      // this warpgroup's decoder MMAs, all of them
-    mbar_wait(bar0 + 8 * (1 + kFbWG), round & 1);
-    tc_fence_after();
+  } else if (warp == 4 * kFbWG + 1) {
+    // =========================== producer warp: TMA mask tiles, frames -> A1 ===========================
+    uint32_t pf[kFbWG];                                  // mask tiles requested per warpgroup, all tiles
+#pragma unroll
+    for (int w = 0; w < kFbWG; ++w) pf[w] = 0;
+    const int items_max = (G + kFbWG - 1) / kFbWG;
+    auto issue_items = [&](int b, int k0, int i_lo, int i_hi) {     // lane 0 only
+      for (int i = i_lo; i < i_hi; ++i)
+#pragma unroll
+        for (int w = 0; w < kFbWG; ++w) {
+          const int g = w + i * kFbWG;
+          if (g >= G) continue;
+          const uint32_t slot = pf[w] % kFbStages, nfill = pf[w] / kFbStages;
+          if (nfill > 0) mbar_wait(SEP_BAR(kBarEmpty + w * kFbStages + slot), (nfill - 1) & 1);
+          const int j = g / C, c = g - j * C;
+          const uint32_t full = SEP_BAR(kBarFull + w * kFbStages + slot);
+          mbar_expect_tx(full, kMaskTile);
+          tma_load_2d(sm0 + kOffWG + w * kWGBytes + 2 * kA2Bytes + slot * kMaskTile, &mask_map, j * kFbChunk,
+                      (b * C + c) * K + k0, full);
+          ++pf[w];
+        }
+    };
+    auto stage_frames = [&](int t) {                     // all 32 lanes: 4 rows each
+      const int b = t / a.tiles, k0 = (t - b * a.tiles) * (kFbM - 1);
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int row = lane + 32 * rr, frame = k0 + row;
+        const float *src = a.wave + static_cast<int64_t>(b) * a.n + static_cast<int64_t>(frame) * kFbHop;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                    // 4 k-chunks of 4 taps
+          const float4 x = frame < K ? __ldg(reinterpret_cast<const float4 *>(src) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 hi, lo;
+          split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y);
+          split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
+          const int o = q * (kFbM / 8) * 128 + (row >> 3) * 128 + (row & 7) * 16;
+          *reinterpret_cast<float4 *>(sm + kOffA1Hi + o) = hi;
+          *reinterpret_cast<float4 *>(sm + kOffA1Lo + o) = lo;
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(SEP_BAR(kBarA1));
+    };
+    if (blockIdx.x < n_tiles) stage_frames(blockIdx.x);
+    uint32_t round = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++round) {
+      const int b = t / a.tiles, k0 = (t - b * a.tiles) * (kFbM - 1);
+      const int i_split = items_max < kFbStages ? items_max : kFbStages;
+      if (lane == 0) issue_items(b, k0, 0, i_split);
+      __syncwarp();
+      if (t + static_cast<int>(gridDim.x) < n_tiles) {
+        mbar_wait(SEP_BAR(kBarG1), round & 1);             // GEMM 1 of this tile has consumed A1
+        stage_frames(t + gridDim.x);
+      }
+      __syncwarp();
+      if (lane == 0) issue_items(b, k0, i_split, items_max);
+      __syncwarp();
+    }
+  } else {
+    // =========================== consumer warpgroups ===========================
+    unsigned char *wgs = sm + kOffWG + wg * kWGBytes;
+    unsigned char *a2hi = wgs, *a2lo = wgs + kA2Bytes, *ring = wgs + 2 * kA2Bytes;
+    float *up = reinterpret_cast<float *>(wgs + 2 * kA2Bytes + kFbStages * kMaskTile);
+    const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16);
+    uint32_t use = 0;                                    // items this warpgroup has written to its A2 buffer
+    uint32_t fills = 0;                                  // mask tiles this warpgroup has consumed
+    uint32_t round = 0;
+    const int sw = (m >> 1) & 3;                         // SWIZZLE_64B: chunk q of row m sits at q ^ ((m >> 1) & 3)
+    const int a2off = (m >> 3) * 128 + (m & 7) * 16;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++round) {
+      const int b = t / a.tiles, tile = t - b * a.tiles;
+      const int k0 = tile * (kFbM - 1);                     // first frame of the tile (1-frame halo)
+      const int frame = k0 + m;
+      const bool row_ok = frame < K;
+      const bool owner = row_ok && (m > 0 || tile == 0);    // row 0 of a later tile is the halo frame
+      mbar_wait(SEP_BAR(kBarG1), round & 1);
+      tc_fence_after();
 
-    // ---- sum of the warpgroups' D2_c -> overlap-add of neighbouring frames -> est ----
-    for (int c = wg; c < C; c += kFbWG) {
-      float y[16];
-#pragma unroll
-      for (int e = 0; e < 16; ++e) y[e] = 0.f;
-      for (int w = 0; w < kFbWG; ++w) {
-        if (!has[w * 4 + c]) continue;
-        float p[16];
-        tmem_ld16(lane_addr + kFbN + kFbL * (w * C + c), p);
-#pragma unroll
-        for (int e = 0; e < 16; ++e) y[e] += p[e];
-      }
-      // hop-block h = frame gets y[frame][0:8] + y[frame-1][8:16]
-#pragma unroll
-      for (int e = 0; e < 8; ++e) up[m * 8 + e] = y[8 + e];
-      wg_sync(wg);
-      float *out = a.est + (static_cast<int64_t>(b) * C + c) * a.est_len;
-      if (owner) {
-        float4 lo4 = make_float4(y[0], y[1], y[2], y[3]), hi4 = make_float4(y[4], y[5], y[6], y[7]);
-        if (m > 0) {
-          const float *p = up + (m - 1) * 8;
-          lo4.x += p[0]; lo4.y += p[1]; lo4.z += p[2]; lo4.w += p[3];
-          hi4.x += p[4]; hi4.y += p[5]; hi4.z += p[6]; hi4.w += p[7];
+      int j = wg / C, c = wg - j * C;                       // work item g = wg, wg + 4, ...: (j, c) kept incrementally
+      for (int g = wg; g < G; g += kFbWG) {
+        float d[kFbChunk];
+        __syncwarp();                                       // tcgen05.ld is warp-collective (.sync.aligned)
+        tmem_ld16(lane_addr + j * kFbChunk, d);
+        if (g + kFbWG >= G) {                               // that was this thread's last read of D1
+          tc_fence_before();
+          mbar_arrive(SEP_BAR(kBarD1Free));
         }
-        float4 *dst = reinterpret_cast<float4 *>(out + static_cast<int64_t>(frame) * kFbHop);
-        dst[0] = lo4;
-        dst[1] = hi4;
-        if (frame == K - 1) {                              // the tail hop-block of the utterance
-          dst[2] = make_float4(y[8], y[9], y[10], y[11]);
-          dst[3] = make_float4(y[12], y[13], y[14], y[15]);
+        // frames beyond the utterance are all-zero rows of A1: their code is relu(0) = 0, so the
+        // (finite) mask values of whatever rows the tile covers there never matter
+#pragma unroll
+        for (int e = 0; e < kFbChunk; ++e) d[e] = fmaxf(d[e], 0.f);
+        const uint32_t slot = fills % kFbStages;
+        mbar_wait(SEP_BAR(kBarFull + wg * kFbStages + slot), (fills / kFbStages) & 1);
+        const unsigned char *mk_s = ring + slot * kMaskTile + m * 64;
+        float2 p[kFbChunk / 2];
+#pragma unroll
+        for (int q = 0; q < kFbChunk / 4; ++q) {
+          const float4 mk = *reinterpret_cast<const float4 *>(mk_s + ((q ^ sw) << 4));
+          p[2 * q] = __fmul2_rn(make_float2(d[4 * q], d[4 * q + 1]), make_float2(mk.x, mk.y));
+          p[2 * q + 1] = __fmul2_rn(make_float2(d[4 * q + 2], d[4 * q + 3]), make_float2(mk.z, mk.w));
         }
+        ++fills;
+        if (use > 0) mbar_wait(SEP_BAR(kBarA2Free + wg), (use - 1) & 1);   // the MMAs that read the A2 buffer are done
+#pragma unroll
+        for (int q = 0; q < kFbChunk / 4; ++q) {
+          float4 hi, lo;
+          hi.x = __uint_as_float(__float_as_uint(p[2 * q].x) & 0xFFFFE000u);
+          hi.y = __uint_as_float(__float_as_uint(p[2 * q].y) & 0xFFFFE000u);
+          hi.z = __uint_as_float(__float_as_uint(p[2 * q + 1].x) & 0xFFFFE000u);
+          hi.w = __uint_as_float(__float_as_uint(p[2 * q + 1].y) & 0xFFFFE000u);
+          const float2 l0 = __fadd2_rn(p[2 * q], make_float2(-hi.x, -hi.y));
+          const float2 l1 = __fadd2_rn(p[2 * q + 1], make_float2(-hi.z, -hi.w));
+          lo = make_float4(l0.x, l0.y, l1.x, l1.y);
+          const int o = q * (kFbM / 8) * 128 + a2off;
+          *reinterpret_cast<float4 *>(a2hi + o) = hi;
+          *reinterpret_cast<float4 *>(a2lo + o) = lo;
+        }
+        ++use;
+        // the shared-memory stores above depend on the mask loads, so the loads have completed: only now
+        // may the producer's TMA (another proxy) overwrite the mask slot
+        mbar_arrive(SEP_BAR(kBarEmpty + wg * kFbStages + slot));
+        fence_async_smem();
+        mbar_arrive(SEP_BAR(kBarA2Ready + wg));
+        if (a.code && owner && c == 0) {                    // optional dump of the unmasked code (tests)
+          float4 *dst = reinterpret_cast<float4 *>(a.code + (static_cast<int64_t>(b) * K + frame) * kFbN + j * kFbChunk);
+#pragma unroll
+          for (int q = 0; q < kFbChunk / 4; ++q) dst[q] = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
+        }
+        c += kFbWG;
+        while (c >= C) { c -= C; ++j; }
       }
-      wg_sync(wg);                                        // `up` is reused by this warpgroup's next source
+
+      // ---- sum of the warpgroups' D2_c -> overlap-add of neighbouring frames -> est ----
+      if (wg < C) {
+        mbar_wait(SEP_BAR(kBarD2), round & 1);
+        tc_fence_after();
+      }
+      for (int cc = wg; cc < C; cc += kFbWG) {
+        float y[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) y[e] = 0.f;
+        for (int w = 0; w < kFbWG; ++w) {
+          if (!has[w * 4 + cc]) continue;
+          float pp[16];
+          __syncwarp();
+          tmem_ld16(lane_addr + kFbN + kFbL * (w * C + cc), pp);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) y[e] += pp[e];
+        }
+        if (cc + kFbWG >= C) {                              // this thread's last read of D2
+          tc_fence_before();
+          mbar_arrive(SEP_BAR(kBarD2Free));
+        }
+        // hop-block h = frame gets y[frame][0:8] + y[frame-1][8:16]
+#pragma unroll
+        for (int e = 0; e < 8; ++e) up[m * 8 + e] = y[8 + e];
+        wg_sync(wg);
+        float *out = a.est + (static_cast<int64_t>(b) * C + cc) * a.est_len;
+        if (owner) {
+          float4 lo4 = make_float4(y[0], y[1], y[2], y[3]), hi4 = make_float4(y[4], y[5], y[6], y[7]);
+          if (m > 0) {
+            const float *pu = up + (m - 1) * 8;
+            lo4.x += pu[0]; lo4.y += pu[1]; lo4.z += pu[2]; lo4.w += pu[3];
+            hi4.x += pu[4]; hi4.y += pu[5]; hi4.z += pu[6]; hi4.w += pu[7];
+          }
+          float4 *dst = reinterpret_cast<float4 *>(out + static_cast<int64_t>(frame) * kFbHop);
+          dst[0] = lo4;
+          dst[1] = hi4;
+          if (frame == K - 1) {                              // the tail hop-block of the utterance
+            dst[2] = make_float4(y[8], y[9], y[10], y[11]);
+            dst[3] = make_float4(y[12], y[13], y[14], y[15]);
+          }
+        }
+        wg_sync(wg);                                        // `up` is reused by this warpgroup's next source
+      }
     }
-    tc_fence_before();                                    // D1 / D2 are overwritten by the next tile
-  }  // tile loop
+  }
+#undef SEP_BAR
 
   tc_fence_before();
   __syncthreads();
