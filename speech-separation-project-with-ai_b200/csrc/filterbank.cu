@@ -40,7 +40,7 @@ constexpr int kFbHop = 8;
 constexpr int kFbChunk = 16;     // code columns per decoder work item
 constexpr int kFbWG = 4;         // warpgroups per CTA; warpgroup w takes work items w, w + 4, ...
 constexpr int kFbThreads = 128 * kFbWG + 64;   // + one MMA-issue warp + one TMA / frame-staging warp
-constexpr int kFbStages = 2;     // mask tiles in flight per warpgroup (TMA ring, one mbarrier per slot)
+constexpr int kFbStages = 4;     // mask tiles in flight per warpgroup (TMA ring, one mbarrier pair per slot)
 
 // ---- shared memory map (bytes) ----
 constexpr int kA1Bytes = kFbM * kFbL * 4;            // 8 KB   [4 k-chunks][16 row groups][128 B]
@@ -51,12 +51,15 @@ constexpr int kMaskTile = kFbM * kFbChunk * 4;       // 8 KB   TMA box [128 rows
 constexpr int kOffA1Hi = 0, kOffA1Lo = kOffA1Hi + kA1Bytes;
 constexpr int kOffB1Hi = kOffA1Lo + kA1Bytes, kOffB1Lo = kOffB1Hi + kB1Bytes;
 constexpr int kOffB2Hi = kOffB1Lo + kB1Bytes, kOffB2Lo = kOffB2Hi + kB2Bytes;
-constexpr int kOffWG = kOffB2Lo + kB2Bytes;          // per warpgroup: A2 hi, A2 lo, mask ring, `up`
-constexpr int kWGBytes = 2 * kA2Bytes + kFbStages * kMaskTile + kFbM * 8 * 4;
+constexpr int kOffWG = kOffB2Lo + kB2Bytes;          // per warpgroup: mask ring, `up`
+constexpr int kWGBytes = kFbStages * kMaskTile + kFbM * 8 * 4;
+// tensor memory columns: D1 [0, 256); D2 [256, 384): 32 columns per source (hi*hi + lo*hi | hi*lo), two
+// tile buffers when C <= 2; masked code A2 of warpgroup w: hi [384 + 32 w), lo + 16
+constexpr int kTmD2 = kFbN, kTmA2 = kFbN + 128;
 constexpr int kOffBar = kOffWG + kFbWG * kWGBytes;   // mbarriers + tmem address + has[][] table
-constexpr int kFbSmem = kOffBar + 512;
+constexpr int kFbSmem = kOffBar + 768;
 
-constexpr uint32_t kLboA1 = 16 * 128, kLboB1 = 32 * 128, kLboB2 = 2 * 128, kLboA2 = 16 * 128, kSbo = 128;
+constexpr uint32_t kLboA1 = 16 * 128, kLboB1 = 32 * 128, kLboB2 = 4 * 128, kSbo = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -77,6 +80,27 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
       :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
+// A operand from tensor memory (lane = row, one 32-bit column per k), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
+      :: "r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// 16 consecutive columns of this thread's TMEM lane <- registers
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&d)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+      :: "r"(taddr), "r"(__float_as_uint(d[0])), "r"(__float_as_uint(d[1])), "r"(__float_as_uint(d[2])),
+         "r"(__float_as_uint(d[3])), "r"(__float_as_uint(d[4])), "r"(__float_as_uint(d[5])),
+         "r"(__float_as_uint(d[6])), "r"(__float_as_uint(d[7])), "r"(__float_as_uint(d[8])),
+         "r"(__float_as_uint(d[9])), "r"(__float_as_uint(d[10])), "r"(__float_as_uint(d[11])),
+         "r"(__float_as_uint(d[12])), "r"(__float_as_uint(d[13])), "r"(__float_as_uint(d[14])),
+         "r"(__float_as_uint(d[15])) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
 }
@@ -180,11 +204,11 @@ enum : int {
   kBarD2 = 1,            // all decoder MMAs of the tile done (commit)
   kBarA1 = 2,            // frames of the tile staged (32 producer lanes)
   kBarD1Free = 3,        // every consumer has read its last D1 chunk (512)
-  kBarD2Free = 4,        // the epilogue has read D2 (128 per source)
+  kBarD2Free = 4,        // [buffer] the epilogue has read D2 (128 per source); buffers alternate per tile when C <= 2
   kBarA2Ready = 8,       // [w] masked code of an item written (128)
   kBarA2Free = 12,       // [w] decoder MMAs of that item done (commit)
   kBarFull = 16,         // [w * stages + s] mask tile landed (TMA transaction)
-  kBarEmpty = 24,        // [w * stages + s] mask tile read by the whole warpgroup (128)
+  kBarEmpty = 32,        // [w * stages + s] mask tile read by the whole warpgroup (128)
 };
 
 __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs a,
@@ -194,8 +218,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
   const int wg = threadIdx.x >> 7, m = threadIdx.x & 127, wq = warp & 3;
   const int K = a.frames, C = a.n_src;
   uint64_t *bars = reinterpret_cast<uint64_t *>(sm + kOffBar);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + kOffBar + 384);
-  unsigned char *has = sm + kOffBar + 400;                         // has[w * 4 + c]: warpgroup w feeds source c
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + kOffBar + 512);
   const uint32_t bar0 = smem_u32(bars), sm0 = smem_u32(sm);
 #define SEP_BAR(i) (bar0 + 8u * static_cast<uint32_t>(i))
   const int G = (kFbN / kFbChunk) * C;
@@ -211,6 +234,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
     mbar_init(SEP_BAR(kBarA1), 32);
     mbar_init(SEP_BAR(kBarD1Free), 128 * kFbWG);
     mbar_init(SEP_BAR(kBarD2Free), 128 * (C < kFbWG ? C : kFbWG));
+    mbar_init(SEP_BAR(kBarD2Free + 1), 128 * (C < kFbWG ? C : kFbWG));
     for (int w = 0; w < kFbWG; ++w) {
       mbar_init(SEP_BAR(kBarA2Ready + w), 128);
       mbar_init(SEP_BAR(kBarA2Free + w), 1);
@@ -220,8 +244,6 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
       }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    for (int i = 0; i < 16; ++i) has[i] = 0;
-    for (int g = 0; g < G; ++g) has[(g % kFbWG) * 4 + g % C] = 1;
   }
 
   // ---- encoder and decoder weights, split hi / lo, canonical layout (once per CTA) ----
@@ -235,10 +257,11 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
     *reinterpret_cast<float *>(sm + kOffB1Hi + o1) = hi;
     *reinterpret_cast<float *>(sm + kOffB1Lo + o1) = lo;
     const int nf = e / kFbL, ll = e % kFbL;
+    // one decoder operand with N = 32 rows: rows 0..15 = hi, rows 16..31 = lo, so that A_hi * [hi | lo]
+    // is ONE MMA (N = 32) and A_lo * hi a second one (N = 16, the first two row groups)
     split_tf32(__ldg(a.dec + e), hi, lo);
-    const int o2 = kmajor_off(ll, nf, kFbL / 8);
-    *reinterpret_cast<float *>(sm + kOffB2Hi + o2) = hi;
-    *reinterpret_cast<float *>(sm + kOffB2Lo + o2) = lo;
+    *reinterpret_cast<float *>(sm + kOffB2Hi + kmajor_off(ll, nf, 2 * kFbL / 8)) = hi;
+    *reinterpret_cast<float *>(sm + kOffB2Hi + kmajor_off(kFbL + ll, nf, 2 * kFbL / 8)) = lo;
   }
   fence_async_smem();
   tc_fence_before();
@@ -273,13 +296,15 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
           }
           umma_commit(SEP_BAR(kBarG1));
         }
-        if (round > 0) {                                 // D2 of the last tile read by its epilogue
-          mbar_wait(SEP_BAR(kBarD2Free), (round - 1) & 1);
+        // D2 buffer of this tile: read by the epilogue of the tile that used it last
+        const uint32_t nbuf = C <= 2 ? 2 : 1, dbuf = round % nbuf, uses = round / nbuf;
+        if (uses > 0) {
+          mbar_wait(SEP_BAR(kBarD2Free + dbuf), (uses - 1) & 1);
           tc_fence_after();
         }
-        uint32_t next[kFbWG], touched[kFbWG];
+        uint32_t next[kFbWG], touched = 0;                // sources whose accumulator D2_c has been started
 #pragma unroll
-        for (int w = 0; w < kFbWG; ++w) { next[w] = 0; touched[w] = 0; }
+        for (int w = 0; w < kFbWG; ++w) next[w] = 0;
         int left = G;
         while (left > 0) {
 #pragma unroll
@@ -288,23 +313,20 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
             if (g >= G || !mbar_try(SEP_BAR(kBarA2Ready + w), served[w] & 1)) continue;
             tc_fence_after();
             const int j = g / C, c = g - j * C;
-            constexpr uint32_t idesc = umma_idesc_tf32(kFbM, kFbL);
-            const uint32_t a2 = sm0 + kOffWG + w * kWGBytes;
-            const uint32_t dcol = tmem + kFbN + kFbL * (w * C + c);
-            uint32_t acc = (touched[w] >> c) & 1u;
+            constexpr uint32_t idesc32 = umma_idesc_tf32(kFbM, 2 * kFbL), idesc16 = umma_idesc_tf32(kFbM, kFbL);
+            // one thread issues every MMA, so they run in issue order: all warpgroups accumulate into D2_c.
+            // D2_c[:, 0:16] += A_hi * B_hi + A_lo * B_hi,  D2_c[:, 16:32] += A_hi * B_lo
+            const uint32_t a2 = tmem + kTmA2 + 32 * w, dcol = tmem + kTmD2 + 2 * kFbL * (dbuf * C + c);
+            const uint32_t boff = sm0 + kOffB2Hi + j * (kFbChunk / 4) * kLboB2;
+            const uint32_t acc0 = (touched >> c) & 1u;
 #pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
-              const uint32_t aoff = a2 + (pass == 1 ? kA2Bytes : 0);
-              const uint32_t boff = sm0 + (pass == 2 ? kOffB2Lo : kOffB2Hi) + j * (kFbChunk / 4) * kLboB2;
+            for (int ks = 0; ks < kFbChunk / 8; ++ks)
+              umma_tf32_ts(dcol, a2 + 8 * ks, umma_desc(boff + ks * 2 * kLboB2, kLboB2, kSbo), idesc32, ks > 0 ? 1u : acc0);
 #pragma unroll
-              for (int ks = 0; ks < kFbChunk / 8; ++ks) {
-                umma_tf32(dcol, umma_desc(aoff + ks * 2 * kLboA2, kLboA2, kSbo),
-                          umma_desc(boff + ks * 2 * kLboB2, kLboB2, kSbo), idesc, acc);
-                acc = 1;
-              }
-            }
+            for (int ks = 0; ks < kFbChunk / 8; ++ks)
+              umma_tf32_ts(dcol, a2 + kFbChunk + 8 * ks, umma_desc(boff + ks * 2 * kLboB2, kLboB2, kSbo), idesc16, 1u);
             umma_commit(SEP_BAR(kBarA2Free + w));
-            touched[w] |= 1u << c;
+            touched |= 1u << c;
             ++next[w];
             ++served[w];
             --left;
@@ -330,7 +352,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
           const int j = g / C, c = g - j * C;
           const uint32_t full = SEP_BAR(kBarFull + w * kFbStages + slot);
           mbar_expect_tx(full, kMaskTile);
-          tma_load_2d(sm0 + kOffWG + w * kWGBytes + 2 * kA2Bytes + slot * kMaskTile, &mask_map, j * kFbChunk,
+          tma_load_2d(sm0 + kOffWG + w * kWGBytes + slot * kMaskTile, &mask_map, j * kFbChunk,
                       (b * C + c) * K + k0, full);
           ++pf[w];
         }
@@ -373,14 +395,14 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
   } else {
     // =========================== consumer warpgroups ===========================
     unsigned char *wgs = sm + kOffWG + wg * kWGBytes;
-    unsigned char *a2hi = wgs, *a2lo = wgs + kA2Bytes, *ring = wgs + 2 * kA2Bytes;
-    float *up = reinterpret_cast<float *>(wgs + 2 * kA2Bytes + kFbStages * kMaskTile);
+    unsigned char *ring = wgs;
+    float *up = reinterpret_cast<float *>(wgs + kFbStages * kMaskTile);
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16);
     uint32_t use = 0;                                    // items this warpgroup has written to its A2 buffer
     uint32_t fills = 0;                                  // mask tiles this warpgroup has consumed
     uint32_t round = 0;
     const int sw = (m >> 1) & 3;                         // SWIZZLE_64B: chunk q of row m sits at q ^ ((m >> 1) & 3)
-    const int a2off = (m >> 3) * 128 + (m & 7) * 16;
+    const uint32_t a2_addr = lane_addr + kTmA2 + 32 * wg;        // this thread's row of the warpgroup's A2 (hi; lo at + 16)
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++round) {
       const int b = t / a.tiles, tile = t - b * a.tiles;
       const int k0 = tile * (kFbM - 1);                     // first frame of the tile (1-frame halo)
@@ -414,26 +436,28 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
           p[2 * q + 1] = __fmul2_rn(make_float2(d[4 * q + 2], d[4 * q + 3]), make_float2(mk.z, mk.w));
         }
         ++fills;
-        if (use > 0) mbar_wait(SEP_BAR(kBarA2Free + wg), (use - 1) & 1);   // the MMAs that read the A2 buffer are done
+        float hi[kFbChunk], lo[kFbChunk];
 #pragma unroll
-        for (int q = 0; q < kFbChunk / 4; ++q) {
-          float4 hi, lo;
-          hi.x = __uint_as_float(__float_as_uint(p[2 * q].x) & 0xFFFFE000u);
-          hi.y = __uint_as_float(__float_as_uint(p[2 * q].y) & 0xFFFFE000u);
-          hi.z = __uint_as_float(__float_as_uint(p[2 * q + 1].x) & 0xFFFFE000u);
-          hi.w = __uint_as_float(__float_as_uint(p[2 * q + 1].y) & 0xFFFFE000u);
-          const float2 l0 = __fadd2_rn(p[2 * q], make_float2(-hi.x, -hi.y));
-          const float2 l1 = __fadd2_rn(p[2 * q + 1], make_float2(-hi.z, -hi.w));
-          lo = make_float4(l0.x, l0.y, l1.x, l1.y);
-          const int o = q * (kFbM / 8) * 128 + a2off;
-          *reinterpret_cast<float4 *>(a2hi + o) = hi;
-          *reinterpret_cast<float4 *>(a2lo + o) = lo;
+        for (int q = 0; q < kFbChunk / 2; ++q) {
+          hi[2 * q] = __uint_as_float(__float_as_uint(p[q].x) & 0xFFFFE000u);
+          hi[2 * q + 1] = __uint_as_float(__float_as_uint(p[q].y) & 0xFFFFE000u);
+          const float2 l2 = __fadd2_rn(p[q], make_float2(-hi[2 * q], -hi[2 * q + 1]));
+          lo[2 * q] = l2.x;
+          lo[2 * q + 1] = l2.y;
         }
-        ++use;
-        // the shared-memory stores above depend on the mask loads, so the loads have completed: only now
-        // may the producer's TMA (another proxy) overwrite the mask slot
+        // hi / lo depend on the mask loads, so those have completed: only now may the producer's TMA
+        // (another proxy) overwrite the mask slot
         mbar_arrive(SEP_BAR(kBarEmpty + wg * kFbStages + slot));
-        fence_async_smem();
+        if (use > 0) {                                       // the MMAs that read A2 are done
+          mbar_wait(SEP_BAR(kBarA2Free + wg), (use - 1) & 1);
+          tc_fence_after();
+        }
+        __syncwarp();
+        tmem_st16(a2_addr, hi);
+        tmem_st16(a2_addr + kFbChunk, lo);
+        tmem_st_wait();
+        ++use;
+        tc_fence_before();
         mbar_arrive(SEP_BAR(kBarA2Ready + wg));
         if (a.code && owner && c == 0) {                    // optional dump of the unmasked code (tests)
           float4 *dst = reinterpret_cast<float4 *>(a.code + (static_cast<int64_t>(b) * K + frame) * kFbN + j * kFbChunk);
@@ -450,20 +474,16 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
         tc_fence_after();
       }
       for (int cc = wg; cc < C; cc += kFbWG) {
-        float y[16];
+        float y[16], y2[16];
+        const uint32_t dbuf = C <= 2 ? (round & 1u) : 0u;
+        __syncwarp();
+        tmem_ld16(lane_addr + kTmD2 + 2 * kFbL * (dbuf * C + cc), y);
+        tmem_ld16(lane_addr + kTmD2 + 2 * kFbL * (dbuf * C + cc) + kFbL, y2);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) y[e] = 0.f;
-        for (int w = 0; w < kFbWG; ++w) {
-          if (!has[w * 4 + cc]) continue;
-          float pp[16];
-          __syncwarp();
-          tmem_ld16(lane_addr + kFbN + kFbL * (w * C + cc), pp);
-#pragma unroll
-          for (int e = 0; e < 16; ++e) y[e] += pp[e];
-        }
+        for (int e = 0; e < 16; ++e) y[e] += y2[e];
         if (cc + kFbWG >= C) {                              // this thread's last read of D2
           tc_fence_before();
-          mbar_arrive(SEP_BAR(kBarD2Free));
+          mbar_arrive(SEP_BAR(kBarD2Free + (C <= 2 ? (round & 1u) : 0u)));
         }
         // hop-block h = frame gets y[frame][0:8] + y[frame-1][8:16]
 #pragma unroll
