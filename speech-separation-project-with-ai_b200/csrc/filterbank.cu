@@ -39,7 +39,7 @@ constexpr int kFbL = 16;         // taps
 constexpr int kFbHop = 8;
 constexpr int kFbChunk = 16;     // code columns per decoder work item
 constexpr int kFbWG = 4;         // warpgroups per CTA; warpgroup w takes work items w, w + 4, ...
-constexpr int kFbThreads = 128 * kFbWG + 64;   // + one MMA-issue warp + one TMA / frame-staging warp
+constexpr int kFbThreads = 128 * kFbWG + 96;   // + two MMA-issue warps + one TMA / frame-staging warp
 constexpr int kFbStages = 4;     // mask tiles in flight per warpgroup (TMA ring, one mbarrier pair per slot)
 
 // ---- shared memory map (bytes) ----
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
   }
   if (threadIdx.x == 0) {
     mbar_init(SEP_BAR(kBarG1), 1);
-    mbar_init(SEP_BAR(kBarD2), 1);
+    mbar_init(SEP_BAR(kBarD2), (C == 2 || C == 4) ? 2 : 1);
     mbar_init(SEP_BAR(kBarA1), 32);
     mbar_init(SEP_BAR(kBarD1Free), 128 * kFbWG);
     mbar_init(SEP_BAR(kBarD2Free), 128 * (C < kFbWG ? C : kFbWG));
@@ -269,18 +269,22 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4 * kFbWG) {
-    // =========================== MMA warp (one lane issues) ===========================
-    if (lane == 0) {
+  // With C = 2 or 4 a warpgroup always feeds the same source (w mod C), so two issuing threads can split the
+  // warpgroups {0, 2} / {1, 3} without ever sharing an accumulator; otherwise one thread issues everything.
+  const int n_mma = (C == 2 || C == 4) ? 2 : 1;
+  if (warp == 4 * kFbWG || warp == 4 * kFbWG + 1) {
+    // =========================== MMA warps (one lane each issues) ===========================
+    const int mt = warp - 4 * kFbWG;
+    if (lane == 0 && mt < n_mma) {
       uint32_t served[kFbWG];                          // items served per warpgroup, all tiles (phase of a2_ready)
 #pragma unroll
       for (int w = 0; w < kFbWG; ++w) served[w] = 0;
       uint32_t round = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++round) {
-        mbar_wait(SEP_BAR(kBarA1), round & 1);                             // frames staged
-        if (round > 0) mbar_wait(SEP_BAR(kBarD1Free), (round - 1) & 1);      // D1 of the last tile drained
-        tc_fence_after();
-        {
+        if (mt == 0) {
+          mbar_wait(SEP_BAR(kBarA1), round & 1);                             // frames staged
+          if (round > 0) mbar_wait(SEP_BAR(kBarD1Free), (round - 1) & 1);      // D1 of the last tile drained
+          tc_fence_after();
           constexpr uint32_t idesc = umma_idesc_tf32(kFbM, kFbN);
           uint32_t acc = 0;
 #pragma unroll
@@ -302,32 +306,39 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
           mbar_wait(SEP_BAR(kBarD2Free + dbuf), (uses - 1) & 1);
           tc_fence_after();
         }
-        uint32_t next[kFbWG], touched = 0;                // sources whose accumulator D2_c has been started
+        uint32_t touched = 0;                             // sources whose accumulator D2_c has been started
+        int gw[kFbWG], jw[kFbWG], cw[kFbWG];              // next work item of each warpgroup: g and its (j, c)
 #pragma unroll
-        for (int w = 0; w < kFbWG; ++w) next[w] = 0;
-        int left = G;
+        for (int w = 0; w < kFbWG; ++w) { gw[w] = w; jw[w] = w / C; cw[w] = w - jw[w] * C; }
+        constexpr uint32_t idesc32 = umma_idesc_tf32(kFbM, 2 * kFbL), idesc16 = umma_idesc_tf32(kFbM, kFbL);
+        const uint64_t bdesc0 = umma_desc(sm0 + kOffB2Hi, kLboB2, kSbo);
+        const uint32_t d2base = tmem + kTmD2 + 2 * kFbL * (dbuf * C);
+        int left = 0;
+#pragma unroll
+        for (int w = 0; w < kFbWG; ++w)
+          if (w % n_mma == mt) left += (G - w + kFbWG - 1) / kFbWG;
         while (left > 0) {
 #pragma unroll
           for (int w = 0; w < kFbWG; ++w) {
-            const int g = w + static_cast<int>(next[w]) * kFbWG;
-            if (g >= G || !mbar_try(SEP_BAR(kBarA2Ready + w), served[w] & 1)) continue;
+            if (w % n_mma != mt || gw[w] >= G || !mbar_try(SEP_BAR(kBarA2Ready + w), served[w] & 1)) continue;
             tc_fence_after();
-            const int j = g / C, c = g - j * C;
-            constexpr uint32_t idesc32 = umma_idesc_tf32(kFbM, 2 * kFbL), idesc16 = umma_idesc_tf32(kFbM, kFbL);
+            const int j = jw[w], c = cw[w];
             // one thread issues every MMA, so they run in issue order: all warpgroups accumulate into D2_c.
             // D2_c[:, 0:16] += A_hi * B_hi + A_lo * B_hi,  D2_c[:, 16:32] += A_hi * B_lo
-            const uint32_t a2 = tmem + kTmA2 + 32 * w, dcol = tmem + kTmD2 + 2 * kFbL * (dbuf * C + c);
-            const uint32_t boff = sm0 + kOffB2Hi + j * (kFbChunk / 4) * kLboB2;
+            const uint32_t a2 = tmem + kTmA2 + 32 * w, dcol = d2base + 2 * kFbL * c;
+            const uint64_t bdesc = bdesc0 + static_cast<uint64_t>((j * (kFbChunk / 4) * kLboB2) >> 4);
             const uint32_t acc0 = (touched >> c) & 1u;
 #pragma unroll
             for (int ks = 0; ks < kFbChunk / 8; ++ks)
-              umma_tf32_ts(dcol, a2 + 8 * ks, umma_desc(boff + ks * 2 * kLboB2, kLboB2, kSbo), idesc32, ks > 0 ? 1u : acc0);
+              umma_tf32_ts(dcol, a2 + 8 * ks, bdesc + ((ks * 2 * kLboB2) >> 4), idesc32, ks > 0 ? 1u : acc0);
 #pragma unroll
             for (int ks = 0; ks < kFbChunk / 8; ++ks)
-              umma_tf32_ts(dcol, a2 + kFbChunk + 8 * ks, umma_desc(boff + ks * 2 * kLboB2, kLboB2, kSbo), idesc16, 1u);
+              umma_tf32_ts(dcol, a2 + kFbChunk + 8 * ks, bdesc + ((ks * 2 * kLboB2) >> 4), idesc16, 1u);
             umma_commit(SEP_BAR(kBarA2Free + w));
             touched |= 1u << c;
-            ++next[w];
+            gw[w] += kFbWG;
+            cw[w] += kFbWG;
+            while (cw[w] >= C) { cw[w] -= C; ++jw[w]; }
             ++served[w];
             --left;
           }
@@ -335,7 +346,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
         umma_commit(SEP_BAR(kBarD2));
       }
     }
-  } else if (warp == 4 * kFbWG + 1) {
+  } else if (warp == 4 * kFbWG + 2) {
     // =========================== producer warp: TMA mask tiles, frames -> A1 ===========================
     uint32_t pf[kFbWG];                                  // mask tiles requested per warpgroup, all tiles
 #pragma unroll
