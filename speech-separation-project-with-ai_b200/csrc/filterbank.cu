@@ -39,7 +39,7 @@ constexpr int kFbL = 16;         // taps
 constexpr int kFbHop = 8;
 constexpr int kFbChunk = 16;     // code columns per decoder work item
 constexpr int kFbWG = 4;         // warpgroups per CTA; warpgroup w takes work items w, w + 4, ...
-constexpr int kFbThreads = 128 * kFbWG + 96;   // + two MMA-issue warps + one TMA / frame-staging warp
+constexpr int kFbThreads = 128 * kFbWG + 128;  // + two MMA-issue warps + a TMA warp + a frame-staging warp
 constexpr int kFbStages = 4;     // mask tiles in flight per warpgroup (TMA ring, one mbarrier pair per slot)
 
 // ---- shared memory map (bytes) ----
@@ -54,7 +54,7 @@ constexpr int kOffB2Hi = kOffB1Lo + kB1Bytes, kOffB2Lo = kOffB2Hi + kB2Bytes;
 constexpr int kOffWG = kOffB2Lo + kB2Bytes;          // per warpgroup: mask ring, `up`
 constexpr int kWGBytes = kFbStages * kMaskTile + kFbM * 8 * 4;
 // tensor memory columns: D1 [0, 256); D2 [256, 384): 32 columns per source (hi*hi + lo*hi | hi*lo), two
-// tile buffers when C <= 2; masked code A2 of warpgroup w: hi [384 + 32 w), lo + 16
+// tile buffers when C <= 2; masked code A2 of warpgroup w: two 8-column buffers at 384 + 32 w + 16 h (hi | lo)
 constexpr int kTmD2 = kFbN, kTmA2 = kFbN + 128;
 constexpr int kOffBar = kOffWG + kFbWG * kWGBytes;   // mbarriers + tmem address + has[][] table
 constexpr int kFbSmem = kOffBar + 768;
@@ -99,6 +99,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&d)[16]) 
          "r"(__float_as_uint(d[9])), "r"(__float_as_uint(d[10])), "r"(__float_as_uint(d[11])),
          "r"(__float_as_uint(d[12])), "r"(__float_as_uint(d[13])), "r"(__float_as_uint(d[14])),
          "r"(__float_as_uint(d[15])) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float *d) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n"
+      :: "r"(taddr), "r"(__float_as_uint(d[0])), "r"(__float_as_uint(d[1])), "r"(__float_as_uint(d[2])),
+         "r"(__float_as_uint(d[3])), "r"(__float_as_uint(d[4])), "r"(__float_as_uint(d[5])),
+         "r"(__float_as_uint(d[6])), "r"(__float_as_uint(d[7])) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -205,8 +212,8 @@ enum : int {
   kBarA1 = 2,            // frames of the tile staged (32 producer lanes)
   kBarD1Free = 3,        // every consumer has read its last D1 chunk (512)
   kBarD2Free = 4,        // [buffer] the epilogue has read D2 (128 per source); buffers alternate per tile when C <= 2
-  kBarA2Ready = 8,       // [w] masked code of an item written (128)
-  kBarA2Free = 12,       // [w] decoder MMAs of that item done (commit)
+  kBarA2Ready = 48,      // [2 w + h] half h (8 code columns) of an item written to A2 buffer h (128)
+  kBarA2Free = 56,       // [2 w + h] the decoder MMAs that read A2 buffer h are done (commit)
   kBarFull = 16,         // [w * stages + s] mask tile landed (TMA transaction)
   kBarEmpty = 32,        // [w * stages + s] mask tile read by the whole warpgroup (128)
 };
@@ -218,7 +225,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
   const int wg = threadIdx.x >> 7, m = threadIdx.x & 127, wq = warp & 3;
   const int K = a.frames, C = a.n_src;
   uint64_t *bars = reinterpret_cast<uint64_t *>(sm + kOffBar);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + kOffBar + 512);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + kOffBar + 640);
   const uint32_t bar0 = smem_u32(bars), sm0 = smem_u32(sm);
 #define SEP_BAR(i) (bar0 + 8u * static_cast<uint32_t>(i))
   const int G = (kFbN / kFbChunk) * C;
@@ -236,8 +243,10 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
     mbar_init(SEP_BAR(kBarD2Free), 128 * (C < kFbWG ? C : kFbWG));
     mbar_init(SEP_BAR(kBarD2Free + 1), 128 * (C < kFbWG ? C : kFbWG));
     for (int w = 0; w < kFbWG; ++w) {
-      mbar_init(SEP_BAR(kBarA2Ready + w), 128);
-      mbar_init(SEP_BAR(kBarA2Free + w), 1);
+      for (int h = 0; h < 2; ++h) {
+        mbar_init(SEP_BAR(kBarA2Ready + 2 * w + h), 128);
+        mbar_init(SEP_BAR(kBarA2Free + 2 * w + h), 1);
+      }
       for (int st = 0; st < kFbStages; ++st) {
         mbar_init(SEP_BAR(kBarFull + w * kFbStages + st), 1);
         mbar_init(SEP_BAR(kBarEmpty + w * kFbStages + st), 128);
@@ -313,61 +322,64 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
         constexpr uint32_t idesc32 = umma_idesc_tf32(kFbM, 2 * kFbL), idesc16 = umma_idesc_tf32(kFbM, kFbL);
         const uint64_t bdesc0 = umma_desc(sm0 + kOffB2Hi, kLboB2, kSbo);
         const uint32_t d2base = tmem + kTmD2 + 2 * kFbL * (dbuf * C);
-        int left = 0;
-#pragma unroll
-        for (int w = 0; w < kFbWG; ++w)
-          if (w % n_mma == mt) left += (G - w + kFbWG - 1) / kFbWG;
-        while (left > 0) {
+        // strict round-robin over this thread's warpgroups, item by item, half by half: the consumers advance
+        // in step, so a blocking wait on the next hand-off in that order almost never waits, and no failed
+        // polls of other warpgroups' barriers sit between two services
+        bool more = true;
+        while (more) {
+          more = false;
 #pragma unroll
           for (int w = 0; w < kFbWG; ++w) {
-            if (w % n_mma != mt || gw[w] >= G || !mbar_try(SEP_BAR(kBarA2Ready + w), served[w] & 1)) continue;
-            tc_fence_after();
+            if (w % n_mma != mt || gw[w] >= G) continue;
             const int j = jw[w], c = cw[w];
-            // one thread issues every MMA, so they run in issue order: all warpgroups accumulate into D2_c.
-            // D2_c[:, 0:16] += A_hi * B_hi + A_lo * B_hi,  D2_c[:, 16:32] += A_hi * B_lo
-            const uint32_t a2 = tmem + kTmA2 + 32 * w, dcol = d2base + 2 * kFbL * c;
-            const uint64_t bdesc = bdesc0 + static_cast<uint64_t>((j * (kFbChunk / 4) * kLboB2) >> 4);
-            const uint32_t acc0 = (touched >> c) & 1u;
+            const uint32_t dcol = d2base + 2 * kFbL * c;
 #pragma unroll
-            for (int ks = 0; ks < kFbChunk / 8; ++ks)
-              umma_tf32_ts(dcol, a2 + 8 * ks, bdesc + ((ks * 2 * kLboB2) >> 4), idesc32, ks > 0 ? 1u : acc0);
-#pragma unroll
-            for (int ks = 0; ks < kFbChunk / 8; ++ks)
-              umma_tf32_ts(dcol, a2 + kFbChunk + 8 * ks, bdesc + ((ks * 2 * kLboB2) >> 4), idesc16, 1u);
-            umma_commit(SEP_BAR(kBarA2Free + w));
-            touched |= 1u << c;
+            for (uint32_t h = 0; h < 2; ++h) {
+              mbar_wait(SEP_BAR(kBarA2Ready + 2 * w + h), (served[w] >> 1) & 1);
+              tc_fence_after();
+              // issuing threads never share an accumulator, and one thread's MMAs run in issue order:
+              // D2_c[:, 0:16] += A_hi * B_hi + A_lo * B_hi,  D2_c[:, 16:32] += A_hi * B_lo
+              const uint32_t a2 = tmem + kTmA2 + 32 * w + 16 * h;
+              const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(((j * (kFbChunk / 4) + 2 * h) * kLboB2) >> 4);
+              umma_tf32_ts(dcol, a2, bdesc, idesc32, (touched >> c) & 1u);
+              umma_tf32_ts(dcol, a2 + 8, bdesc, idesc16, 1u);
+              umma_commit(SEP_BAR(kBarA2Free + 2 * w + h));
+              touched |= 1u << c;
+              ++served[w];
+            }
             gw[w] += kFbWG;
             cw[w] += kFbWG;
             while (cw[w] >= C) { cw[w] -= C; ++jw[w]; }
-            ++served[w];
-            --left;
+            more = more || gw[w] < G;
           }
         }
         umma_commit(SEP_BAR(kBarD2));
       }
     }
   } else if (warp == 4 * kFbWG + 2) {
-    // =========================== producer warp: TMA mask tiles, frames -> A1 ===========================
-    uint32_t pf[kFbWG];                                  // mask tiles requested per warpgroup, all tiles
-#pragma unroll
-    for (int w = 0; w < kFbWG; ++w) pf[w] = 0;
-    const int items_max = (G + kFbWG - 1) / kFbWG;
-    auto issue_items = [&](int b, int k0, int i_lo, int i_hi) {     // lane 0 only
-      for (int i = i_lo; i < i_hi; ++i)
-#pragma unroll
-        for (int w = 0; w < kFbWG; ++w) {
-          const int g = w + i * kFbWG;
-          if (g >= G) continue;
-          const uint32_t slot = pf[w] % kFbStages, nfill = pf[w] / kFbStages;
+    // =========================== producer warp: mask tiles by TMA ===========================
+    // lane w feeds warpgroup w on its own: a slow warpgroup never delays the mask tiles of another one
+    if (lane < kFbWG) {
+      const int w = lane;
+      uint32_t pf = 0;                                   // mask tiles requested for this warpgroup, all tiles
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int b = t / a.tiles, k0 = (t - b * a.tiles) * (kFbM - 1);
+        int j = w / C, c = w - j * C;
+        for (int g = w; g < G; g += kFbWG) {
+          const uint32_t slot = pf % kFbStages, nfill = pf / kFbStages;
           if (nfill > 0) mbar_wait(SEP_BAR(kBarEmpty + w * kFbStages + slot), (nfill - 1) & 1);
-          const int j = g / C, c = g - j * C;
           const uint32_t full = SEP_BAR(kBarFull + w * kFbStages + slot);
           mbar_expect_tx(full, kMaskTile);
           tma_load_2d(sm0 + kOffWG + w * kWGBytes + slot * kMaskTile, &mask_map, j * kFbChunk,
                       (b * C + c) * K + k0, full);
-          ++pf[w];
+          ++pf;
+          c += kFbWG;
+          while (c >= C) { c -= C; ++j; }
         }
-    };
+      }
+    }
+  } else if (warp == 4 * kFbWG + 3) {
+    // =========================== frame-staging warp: the next tile's frames -> A1 (hi / lo) ===========================
     auto stage_frames = [&](int t) {                     // all 32 lanes: 4 rows each
       const int b = t / a.tiles, k0 = (t - b * a.tiles) * (kFbM - 1);
 #pragma unroll
@@ -390,18 +402,9 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
     };
     if (blockIdx.x < n_tiles) stage_frames(blockIdx.x);
     uint32_t round = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++round) {
-      const int b = t / a.tiles, k0 = (t - b * a.tiles) * (kFbM - 1);
-      const int i_split = items_max < kFbStages ? items_max : kFbStages;
-      if (lane == 0) issue_items(b, k0, 0, i_split);
-      __syncwarp();
-      if (t + static_cast<int>(gridDim.x) < n_tiles) {
-        mbar_wait(SEP_BAR(kBarG1), round & 1);             // GEMM 1 of this tile has consumed A1
-        stage_frames(t + gridDim.x);
-      }
-      __syncwarp();
-      if (lane == 0) issue_items(b, k0, i_split, items_max);
-      __syncwarp();
+    for (int t = blockIdx.x; t + static_cast<int>(gridDim.x) < n_tiles; t += gridDim.x, ++round) {
+      mbar_wait(SEP_BAR(kBarG1), round & 1);               // GEMM 1 of this tile has consumed A1
+      stage_frames(t + gridDim.x);
     }
   } else {
     // =========================== consumer warpgroups ===========================
@@ -413,7 +416,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
     uint32_t fills = 0;                                  // mask tiles this warpgroup has consumed
     uint32_t round = 0;
     const int sw = (m >> 1) & 3;                         // SWIZZLE_64B: chunk q of row m sits at q ^ ((m >> 1) & 3)
-    const uint32_t a2_addr = lane_addr + kTmA2 + 32 * wg;        // this thread's row of the warpgroup's A2 (hi; lo at + 16)
+    const uint32_t a2_addr = lane_addr + kTmA2 + 32 * wg;        // this thread's row of the warpgroup's A2: buffer h at + 16 h (hi 8 columns, lo 8 columns)
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++round) {
       const int b = t / a.tiles, tile = t - b * a.tiles;
       const int k0 = tile * (kFbM - 1);                     // first frame of the tile (1-frame halo)
@@ -456,20 +459,28 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
           lo[2 * q] = l2.x;
           lo[2 * q + 1] = l2.y;
         }
-        // hi / lo depend on the mask loads, so those have completed: only now may the producer's TMA
-        // (another proxy) overwrite the mask slot
+        // The producer's TMA (another proxy) may overwrite the mask slot only after this thread's loads from it
+        // have COMPLETED, and an mbarrier arrive does not wait for loads that were merely issued.  A shared-memory
+        // store of a value that depends on all four loads cannot issue before they return, and the arrive cannot
+        // move above a store: that is the ordering.  (`up` is idle until the epilogue.)
+        up[m] = (p[0].x + p[2].x) + (p[4].x + p[6].x);
         mbar_arrive(SEP_BAR(kBarEmpty + wg * kFbStages + slot));
-        if (use > 0) {                                       // the MMAs that read A2 are done
-          mbar_wait(SEP_BAR(kBarA2Free + wg), (use - 1) & 1);
-          tc_fence_after();
+        // two half items (8 code columns each) into the two A2 buffers: the wait is for the MMAs of the
+        // previous ITEM's half, committed a whole item ago
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (use > 0) {
+            mbar_wait(SEP_BAR(kBarA2Free + 2 * wg + h), (use - 1) & 1);
+            tc_fence_after();
+          }
+          __syncwarp();
+          tmem_st8(a2_addr + 16 * h, hi + 8 * h);
+          tmem_st8(a2_addr + 16 * h + 8, lo + 8 * h);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(SEP_BAR(kBarA2Ready + 2 * wg + h));
         }
-        __syncwarp();
-        tmem_st16(a2_addr, hi);
-        tmem_st16(a2_addr + kFbChunk, lo);
-        tmem_st_wait();
         ++use;
-        tc_fence_before();
-        mbar_arrive(SEP_BAR(kBarA2Ready + wg));
         if (a.code && owner && c == 0) {                    // optional dump of the unmasked code (tests)
           float4 *dst = reinterpret_cast<float4 *>(a.code + (static_cast<int64_t>(b) * K + frame) * kFbN + j * kFbChunk);
 #pragma unroll
@@ -554,7 +565,7 @@ static int make_mask_map(CUtensorMap *map, const float *masks, uint64_t rows) {
   const cuuint32_t box[2] = {kFbChunk, kFbM}, elem[2] = {1, 1};
   const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(masks), dims, strides, box,
                             elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
     return SEP_ERR_CUDA;
