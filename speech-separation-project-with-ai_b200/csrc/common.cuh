@@ -89,7 +89,20 @@ struct Scratch {
   // optional caller-provided arena (no allocation inside the call: CUDA graphs)
   unsigned char *arena = nullptr;
   size_t arena_bytes = 0, arena_used = 0;
-  explicit Scratch(cudaStream_t s) : stream(s) {}
+  explicit Scratch(cudaStream_t s) : stream(s) { keep_pool_cached(); }
+  // Stream-ordered frees go back to the device's default pool, not to the driver: without this every call
+  // pays hundreds of microseconds of cudaMallocAsync (set once per process and device).
+  static void keep_pool_cached() {
+    static thread_local int done_for = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done_for = dev;
+  }
   ~Scratch() {
     for (void *p : blocks) cudaFreeAsync(p, stream);
   }

@@ -172,8 +172,10 @@ static int run_score(const float *d_refs, const float *d_ests, const int64_t *d_
   int rc;
   if ((rc = s.alloc(&partials, static_cast<size_t>(items) * NV))) return rc;
   if (items > 0) {
+    profile_begin(stream);
     score_chunk_kernel<C><<<items, kScoreThreads, 0, stream>>>(d_refs, d_ests, d_roff, d_eoff, d_len,
                                                                d_start, batch, partials);
+    profile_end(stream);
     SEP_LAUNCHED();
   }
   score_finalize_kernel<C><<<batch, 32, 0, stream>>>(partials, d_start, d_scores);
@@ -183,6 +185,31 @@ static int run_score(const float *d_refs, const float *d_ests, const int64_t *d_
     SEP_LAUNCHED();
   }
   return SEP_OK;
+}
+
+// Pinned staging for per-call metadata: a small per-thread ring; a slot is reused only after the copy that
+// read it has completed (event), so entry points can stay asynchronous.
+struct MetaSlot { void *host = nullptr; size_t cap = 0; cudaEvent_t copied = nullptr; };
+static MetaSlot *meta_slot(size_t bytes) {
+  static thread_local MetaSlot ring[4];
+  static thread_local unsigned next = 0;
+  MetaSlot &m = ring[next++ % 4];
+  if (m.copied == nullptr) {
+    if (cudaEventCreateWithFlags(&m.copied, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  } else if (cudaEventSynchronize(m.copied) != cudaSuccess) {
+    return nullptr;
+  }
+  if (m.cap < bytes) {
+    if (m.host) cudaFreeHost(m.host);
+    m.host = nullptr;
+    m.cap = 0;
+    if (cudaMallocHost(&m.host, bytes + bytes / 2) != cudaSuccess) {
+      set_error("sep_score_batch_f32: cannot allocate %zu bytes of pinned staging memory", bytes);
+      return nullptr;
+    }
+    m.cap = bytes + bytes / 2;
+  }
+  return &m;
 }
 
 }  // namespace sep
@@ -203,7 +230,15 @@ extern "C" int sep_score_batch_f32(const float *refs, const float *ests, const i
   int rc = check_mem(mem);
   if (rc) return rc;
   const int C = n_src;
-  std::vector<int32_t> start(batch + 1, 0);
+  // All metadata travels in ONE pinned staging buffer (ring of 4, reused once its copy has completed), so
+  // the call never blocks on the stream: [ref_off B*C | est_off B*C | lengths B] int64, [chunk_start B+1] int32.
+  const size_t n_off = static_cast<size_t>(batch) * C;
+  const size_t meta_bytes = (2 * n_off + batch) * sizeof(int64_t) + (static_cast<size_t>(batch) + 1) * sizeof(int32_t);
+  MetaSlot *slot = meta_slot(meta_bytes);
+  if (!slot) return SEP_ERR_NOMEM;
+  int64_t *h_roff = static_cast<int64_t *>(slot->host), *h_eoff = h_roff + n_off, *h_len = h_eoff + n_off;
+  int32_t *start = reinterpret_cast<int32_t *>(h_len + batch);
+  start[0] = 0;
   for (int b = 0; b < batch; ++b) {
     SEP_REQUIRE(lengths[b] >= 0, "sep_score_batch_f32: negative length at %d", b);
     for (int c = 0; c < C; ++c) {
@@ -211,7 +246,10 @@ extern "C" int sep_score_batch_f32(const float *refs, const float *ests, const i
                   "sep_score_batch_f32: reference %d/%d out of bounds", b, c);
       SEP_REQUIRE(est_offsets[b * C + c] >= 0 && est_offsets[b * C + c] + lengths[b] <= total_est,
                   "sep_score_batch_f32: estimate %d/%d out of bounds", b, c);
+      h_roff[b * C + c] = ref_offsets[b * C + c];
+      h_eoff[b * C + c] = est_offsets[b * C + c];
     }
+    h_len[b] = lengths[b];
     const int64_t chunks = (lengths[b] + kScoreChunk - 1) / kScoreChunk;
     SEP_REQUIRE(start[b] + chunks < INT32_MAX, "sep_score_batch_f32: batch too large");
     start[b + 1] = start[b] + static_cast<int32_t>(chunks);
@@ -220,12 +258,12 @@ extern "C" int sep_score_batch_f32(const float *refs, const float *ests, const i
   const float *d_refs, *d_ests;
   if ((rc = stage_in(s, refs, static_cast<size_t>(total_ref), mem, &d_refs))) return rc;
   if ((rc = stage_in(s, ests, static_cast<size_t>(total_est), mem, &d_ests))) return rc;
-  const int64_t *d_roff, *d_eoff, *d_len;
-  const int32_t *d_start;
-  if ((rc = stage_in(s, ref_offsets, static_cast<size_t>(batch) * C, SEP_MEM_HOST, &d_roff))) return rc;
-  if ((rc = stage_in(s, est_offsets, static_cast<size_t>(batch) * C, SEP_MEM_HOST, &d_eoff))) return rc;
-  if ((rc = stage_in(s, lengths, static_cast<size_t>(batch), SEP_MEM_HOST, &d_len))) return rc;
-  if ((rc = stage_in(s, static_cast<const int32_t *>(start.data()), start.size(), SEP_MEM_HOST, &d_start))) return rc;
+  unsigned char *d_meta;
+  if ((rc = s.alloc(&d_meta, meta_bytes))) return rc;
+  SEP_CUDA(cudaMemcpyAsync(d_meta, slot->host, meta_bytes, cudaMemcpyHostToDevice, stream));
+  SEP_CUDA(cudaEventRecord(slot->copied, stream));
+  const int64_t *d_roff = reinterpret_cast<const int64_t *>(d_meta), *d_eoff = d_roff + n_off, *d_len = d_eoff + n_off;
+  const int32_t *d_start = reinterpret_cast<const int32_t *>(d_len + batch);
   double *d_scores, *d_sums;
   const size_t n_scores = static_cast<size_t>(batch) * (2 * C * C + 4);
   if ((rc = stage_out(s, scores, n_scores, mem, &d_scores))) return rc;
@@ -240,10 +278,7 @@ extern "C" int sep_score_batch_f32(const float *refs, const float *ests, const i
   if (rc) return rc;
   if ((rc = copy_back(s, scores, d_scores, n_scores, mem))) return rc;
   if ((rc = copy_back(s, sums, d_sums, static_cast<size_t>(3), mem))) return rc;
-  // the staged metadata lives in `start` (host vector): make sure the copies
-  // are done before it goes out of scope
-  SEP_CUDA(cudaStreamSynchronize(stream));
-  return SEP_OK;
+  return finish(s, mem);      // device mode: asynchronous (the metadata sits in the pinned ring)
 }
 
 // pow_norm / pow_np_norm (metrics/evaluate_metrics.py:14-20): sum(a * b) in float64.
