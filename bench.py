@@ -56,7 +56,7 @@ def parse_args():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--shift", type=int, default=128)
     ap.add_argument("--window", default="blackman", choices=["blackman", "hann", "hamming"])
-    ap.add_argument("--streams", type=int, default=3,
+    ap.add_argument("--streams", type=int, default=6,
                     help="independent steps captured round-robin on this many streams inside the graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

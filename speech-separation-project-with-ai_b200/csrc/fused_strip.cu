@@ -62,7 +62,7 @@ struct StripGeom {
 };
 
 template <int C, int R, bool SCORE, int W>
-__global__ void __launch_bounds__(W * 32, 1) strip256_kernel(const FusedArgs a) {
+__global__ void __launch_bounds__(W * 32, 8 / W) strip256_kernel(const FusedArgs a) {
   using G = StripGeom<C, R, SCORE, W>;
   constexpr int SHIFT = G::SHIFT, H = G::H, NSIG = G::NSIG, D = G::D, NY = G::NY, NOUT = G::NOUT;
   constexpr int NSLOT = G::NSLOT, SPAN = G::SPAN, SSK = G::SPAN_SK, US = G::UNIT_STRIDE, NV = G::NV;
@@ -391,7 +391,8 @@ static int launch_strip_w(const sep_plan *p, FusedArgs a, int batch, double *d_s
                           Scratch &s, cudaStream_t stream) {
   using G = StripGeom<C, R, SCORE, W>;
   const int sms = p->sm_count > 0 ? p->sm_count : 148;
-  pick_strips(a.T, G::H, 4, batch, sms * W, &a.tiles, &a.strip_iters);
+  constexpr int CTAS_PER_SM = 8 / W;                // 8 warps per SM either way
+  pick_strips(a.T, G::H, 4, batch, sms * 8, &a.tiles, &a.strip_iters);
   int rc;
   double *partials = nullptr;
   int *counters = nullptr;
@@ -414,7 +415,7 @@ static int launch_strip_w(const sep_plan *p, FusedArgs a, int batch, double *d_s
   SEP_CUDA(cudaFuncSetAttribute(strip256_kernel<C, R, SCORE, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
   const int64_t total = static_cast<int64_t>(batch) * a.tiles;
-  const int grid = static_cast<int>(std::min<int64_t>(sms, total));
+  const int grid = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(sms) * CTAS_PER_SM, (total + W - 1) / W));
   profile_begin(stream);
   strip256_kernel<C, R, SCORE, W><<<grid, W * 32, smem, stream>>>(a);
   profile_end(stream);
@@ -427,7 +428,15 @@ template <int C, int R, bool SCORE>
 static int launch_strip(const sep_plan *p, const FusedArgs &a, int batch, double *d_scores, double *d_sums,
                         Scratch &s, cudaStream_t stream) {
   // 12 warps (168 registers) were measured slower: the spills miss the small L1 left beside 200 KB of shared memory
-  return launch_strip_w<C, R, SCORE, 8>(p, a, batch, d_scores, d_sums, s, stream);
+  // two 4-warp CTAs per SM (104 KB each) instead of one 8-warp CTA: CTAs of the NEXT launch (another stream
+  // of the replayed graph) move in as soon as four warps are done, not eight
+  static const int warps = [] { const char *e = getenv("SEPCORE_STRIP_WARPS"); return e ? atoi(e) : 4; }();
+  switch (warps) {
+    case 1: return launch_strip_w<C, R, SCORE, 1>(p, a, batch, d_scores, d_sums, s, stream);
+    case 2: return launch_strip_w<C, R, SCORE, 2>(p, a, batch, d_scores, d_sums, s, stream);
+    case 8: return launch_strip_w<C, R, SCORE, 8>(p, a, batch, d_scores, d_sums, s, stream);
+    default: return launch_strip_w<C, R, SCORE, 4>(p, a, batch, d_scores, d_sums, s, stream);
+  }
 }
 
 template <int C>

@@ -44,7 +44,7 @@ struct Strip512Geom {
 };
 
 template <int C, bool SCORE, int W>
-__global__ void __launch_bounds__(W * 32, 1) strip512_kernel(const FusedArgs a) {
+__global__ void __launch_bounds__(W * 32, 8 / W) strip512_kernel(const FusedArgs a) {
   using G = Strip512Geom<C, SCORE, W>;
   constexpr int SHIFT = G::SHIFT, H = G::H, NSIG = G::NSIG, SPAN = G::SPAN, NV = G::NV;
   constexpr int MROW = G::MASK_ROW, MFRAME = G::MASK_FRAME, BINS = G::BINS;
@@ -405,10 +405,11 @@ __global__ void __launch_bounds__(W * 32, 1) strip512_kernel(const FusedArgs a) 
 template <int C, bool SCORE>
 static int launch_strip512(const sep_plan *p, FusedArgs a, int batch, double *d_scores, double *d_sums,
                            Scratch &s, cudaStream_t stream) {
-  constexpr int W = 8;
+  // two 4-warp CTAs per SM (<= 112 KB each): CTAs of the next launch move in as soon as four warps are done
+  constexpr int W = 4, CTAS_PER_SM = 8 / W;
   using G = Strip512Geom<C, SCORE, W>;
   const int sms = p->sm_count > 0 ? p->sm_count : 148;
-  pick_strips(a.T, G::H, G::FPI, batch, sms * W, &a.tiles, &a.strip_iters);
+  pick_strips(a.T, G::H, G::FPI, batch, sms * 8, &a.tiles, &a.strip_iters);
   int rc;
   double *partials = nullptr;
   int *counters = nullptr;
@@ -429,7 +430,7 @@ static int launch_strip512(const sep_plan *p, FusedArgs a, int batch, double *d_
   SEP_CUDA(cudaFuncSetAttribute(strip512_kernel<C, SCORE, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
   const int64_t total = static_cast<int64_t>(batch) * a.tiles;
-  const int grid = static_cast<int>(std::min<int64_t>(sms, total));
+  const int grid = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(sms) * CTAS_PER_SM, (total + W - 1) / W));
   profile_begin(stream);
   strip512_kernel<C, SCORE, W><<<grid, W * 32, smem, stream>>>(a);
   profile_end(stream);
