@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(W * 32, 8 / W) strip256_kernel(const FusedArgs
               const float2 p = __ffma2_rn(XR[r], XR[r], __fmul2_rn(XI[r], XI[r]));
               pmin = fminf(pmin, fminf(p.x, p.y));
               // |X| = 0 -> a finite 1/|X| (and |X| * 1/|X| = 0); the exact-zero label is redone below
-              inv[r] = make_float2(rsqrtf(fmaxf(p.x, 1e-36f)), rsqrtf(fmaxf(p.y, 1e-36f)));
+              inv[r] = make_float2(rsqrt_fast(fmaxf(p.x, 1e-36f)), rsqrt_fast(fmaxf(p.y, 1e-36f)));
               mag[r] = __fmul2_rn(__fmul2_rn(p, inv[r]), gate2);
             }
           }
@@ -258,7 +258,9 @@ __global__ void __launch_bounds__(W * 32, 8 / W) strip256_kernel(const FusedArgs
       const int64_t room = a.n - gb, room_v = n_valid - gb;
       const int lim = room <= 0 ? 0 : static_cast<int>(min(static_cast<int64_t>(NOUT), (room + 15) >> 4));
       const int lim_v = room_v <= 0 ? 0 : static_cast<int>(min(static_cast<int64_t>(NOUT), (room_v + 15) >> 4));
-      const bool plain = skip == 0 && lim_v == NOUT;
+      // one path per warp: if either half-warp has an edge, both take the predicated path (instead of the
+      // two paths running one after the other)
+      const bool plain = !__any_sync(0xffffffffu, !(skip == 0 && lim_v == NOUT));
 #pragma unroll 1
       for (int q = 0; q < C; ++q) {
         {

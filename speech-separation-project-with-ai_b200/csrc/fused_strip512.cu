@@ -213,12 +213,12 @@ __global__ void __launch_bounds__(W * 32, 8 / W) strip512_kernel(const FusedArgs
               if (SCORE) {
                 const float p = fmaf(Sx.x, Sx.x, Sx.y * Sx.y);
                 pmin = fminf(pmin, p);
-                inv[rr] = rsqrtf(fmaxf(p, 1e-36f));
+                inv[rr] = rsqrt_fast(fmaxf(p, 1e-36f));
                 mag[rr] = p * inv[rr] * gate;
                 if (rr == 0) {
                   const float p16 = fmaf(X[16].x, X[16].x, X[16].y * X[16].y);
                   pmin = fminf(pmin, l16 == 0 ? p16 : 1.f);
-                  inv[16] = rsqrtf(fmaxf(p16, 1e-36f));
+                  inv[16] = rsqrt_fast(fmaxf(p16, 1e-36f));
                   mag[16] = p16 * inv[16] * gate;
                 }
               }
