@@ -226,6 +226,18 @@ int sep_filterbank_separate_f32(const float *wave, const float *enc, const float
                                 int taps, int n_filters, int stride, float *est, float *code,
                                 int mem, void *stream);
 
+/* ---- sample formats either side of the path ---- */
+/* int16 PCM -> float32 as wavread / librosa.load deliver the reference's 16-bit wavs
+ * (metrics/evaluate_metrics.py:7-12, parallel_stft.py:213): out[i] = pcm[i] / 32768. */
+int sep_pcm16_to_f32(const int16_t *pcm, int64_t n, float *out, int mem, void *stream);
+
+/* audiowrite's sample conversion (uPIT_baseline.ipynb:1317-1354, cell 40) for float32 data
+ * [batch, n], row by row: optional peak normalisation (data /= max|data|), data *= 32767,
+ * clipped[row] = count(data > 32767), clip to [-32768, 32767], truncate to int16.
+ * clipped may be NULL.  Arithmetic is float32 like numpy's on a float32 array. */
+int sep_audiowrite_i16_f32(const float *data, int batch, int64_t n, int normalize, int16_t *out,
+                           int64_t *clipped, int mem, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

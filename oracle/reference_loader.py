@@ -79,6 +79,25 @@ def load():
     scope = {"np": np, "scipy": scipy, "signal": scipy.signal, "irfft": np.fft.irfft}
     for cell in (38, 39):
         exec("".join(nb["cells"][cell]["source"]), scope)
+    # cell 40: audiowrite -- run unmodified, with the wav writer replaced by a capture
+    import threading
+    captured = {}
+
+    def _capture(path, samplerate, data):
+        captured["data"] = np.array(data, copy=True)
+
+    if not hasattr(np, "float"):
+        np.float = float
+    scope40 = {"np": np, "threading": threading, "wav_write": _capture}
+    exec("".join(nb["cells"][40]["source"]), scope40)
+
+    def audiowrite_int16(data, normalize=False):
+        import contextlib
+        import io
+
+        with contextlib.redirect_stdout(io.StringIO()):
+            clipped = scope40["audiowrite"](data, "unused.wav", 16000, normalize, False)
+        return captured["data"], int(clipped)
 
     ns = types.SimpleNamespace(
         stft=ps.stft,
@@ -91,6 +110,7 @@ def load():
         permute_si_sdr=em.permute_si_sdr,
         pow_norm=em.pow_norm,
         pow_np_norm=em.pow_np_norm,
+        audiowrite_int16=audiowrite_int16,
     )
     _cache["ns"] = ns
     return ns

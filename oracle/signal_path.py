@@ -582,3 +582,52 @@ def separate_and_score(mix, refs, masks, size=256, shift=128, window=None,
                    for i in range(n_src)])
     return {"spec": spec, "labels": labels, "cleaned": cleaned, "ests": ests,
             "pit": pit, "si_sdr_pair": si}
+
+
+# ----------------------------------------------------------------- 8f rank 3: sample formats
+def pcm16_to_float32(pcm):
+    """int16 PCM -> float32 as sf.read(dtype='float32') / librosa.load give it for 16-bit
+    wavs (metrics/evaluate_metrics.py:7-12, parallel_stft.py:213)."""
+    return (np.asarray(pcm, dtype=np.int16).astype(np.float32) / np.float32(32768.0)).astype(np.float32)
+
+
+def audiowrite_int16(data, normalize=False):
+    """The conversion inside audiowrite (uPIT_baseline.ipynb:1331-1346, cell 40), without the
+    file write: returns (int16 samples, number of clipped samples).  `np.float` in the
+    reference is the removed alias of float (only reached for integer input)."""
+    data = np.array(data, copy=True)
+    int16_max = np.iinfo(np.int16).max
+    int16_min = np.iinfo(np.int16).min
+    if normalize:
+        if not data.dtype.kind == 'f':
+            data = data.astype(float)
+        data /= np.max(np.abs(data))
+    if data.dtype.kind == 'f':
+        data *= int16_max
+    sample_to_clip = int(np.sum(data > int16_max))
+    data = np.clip(data, int16_min, int16_max)
+    return data.astype(np.int16), sample_to_clip
+
+
+# ----------------------------------------------------------------- 8f rank 4: TF-style SI-SDR
+def sisdr_values(y_true, y_pred):
+    """SiSdr.update_state's `values` (vq-vae_for_1d_data.ipynb cell 13 :398-421), float32 like TF:
+    y_true [B, L + 1, 1] (last row = length), y_pred [B, L', 1]; cut to the shorter of L, L'."""
+    y_true = np.asarray(y_true, dtype=np.float32)
+    y_pred = np.asarray(y_pred, dtype=np.float32)
+    labels = y_true[:, :-1, :]
+    label_size, pred_size = labels.shape[1], y_pred.shape[1]
+    if label_size < pred_size:
+        y_pred = y_pred[:, :label_size, :]
+    elif label_size > pred_size:
+        labels = labels[:, :pred_size, :]
+    dot = np.matmul(np.transpose(y_pred, (0, 2, 1)), labels)                    # [B, 1, 1]
+    target = dot * labels / np.square(np.linalg.norm(labels, axis=1))[..., None]
+    noise = y_pred - target
+    values = 10 * np.log10(np.square(np.linalg.norm(target, axis=1)) / np.square(np.linalg.norm(noise, axis=1)))
+    return values.reshape(-1)
+
+
+def custom_sisdr_loss(y_true, y_pred):
+    """cell 14 :457-469.  (The loss does not cut the sequences: equal lengths expected.)"""
+    return -float(np.mean(sisdr_values(y_true, y_pred)))

@@ -1,0 +1,165 @@
+// pcm.cu -- the sample-format steps either side of the path:
+//   * int16 PCM -> float32 (what wavread / librosa.load give for the reference's 16-bit wavs:
+//     metrics/evaluate_metrics.py:7-12, parallel_stft.py:213): x / 32768
+//   * audiowrite's float -> int16 conversion (uPIT_baseline.ipynb:1317-1354, cell 40), per row:
+//       if normalize: data /= max(|data|)          (float32 division)
+//       data *= 32767                              (float32 product)
+//       clipped = count(data > 32767);  data = clip(data, -32768, 32767);  int16 = trunc(data)
+// Both are HBM-bound streams: 6 bytes per sample (+ 4 for the max pass when normalising).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace sep {
+
+__global__ void pcm16_to_f32_kernel(const int16_t *__restrict__ pcm, int64_t n, float *__restrict__ out) {
+  const int64_t i0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (i0 + 8 <= n && ((reinterpret_cast<uintptr_t>(pcm) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(pcm + i0));
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[2 * k] = static_cast<float>(static_cast<int16_t>(w[k] & 0xFFFFu)) * (1.f / 32768.f);
+      v[2 * k + 1] = static_cast<float>(static_cast<int16_t>(w[k] >> 16)) * (1.f / 32768.f);
+    }
+    reinterpret_cast<float4 *>(out + i0)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4 *>(out + i0)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    for (int64_t i = i0; i < min(i0 + 8, n); ++i) out[i] = static_cast<float>(pcm[i]) * (1.f / 32768.f);
+  }
+}
+
+// |x| as an unsigned integer is monotonic in |x| (NaN sorts above everything, like numpy's max propagates it)
+template <bool VEC>
+__global__ void row_absmax_kernel(const float *__restrict__ data, int64_t n, unsigned *__restrict__ rowmax) {
+  const int row = blockIdx.y;
+  const float *src = data + static_cast<int64_t>(row) * n;
+  unsigned m = 0;
+  constexpr int V = VEC ? 4 : 1;
+  for (int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * V; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x * V) {
+    if (VEC) {
+      const float4 v = __ldg(reinterpret_cast<const float4 *>(src + i));
+      m = max(max(m, __float_as_uint(v.x) & 0x7FFFFFFFu), __float_as_uint(v.y) & 0x7FFFFFFFu);
+      m = max(max(m, __float_as_uint(v.z) & 0x7FFFFFFFu), __float_as_uint(v.w) & 0x7FFFFFFFu);
+    } else {
+      m = max(m, __float_as_uint(__ldg(src + i)) & 0x7FFFFFFFu);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(rowmax + row, m);
+}
+
+__device__ __forceinline__ int16_t audiowrite_one(float v, bool norm, float peak, unsigned &over) {
+  if (norm) v = __fdiv_rn(v, peak);                  // data /= np.max(np.abs(data)), :1337
+  v = __fmul_rn(v, 32767.f);                         // data *= int16_max, :1340
+  over += v > 32767.f;                               // :1342
+  v = fminf(fmaxf(v, -32768.f), 32767.f);            // np.clip, :1345
+  return static_cast<int16_t>(static_cast<int>(v));  // astype(np.int16): toward zero
+}
+
+// VEC: n % 8 == 0 and 16-byte aligned rows -> two float4 loads, one 16-byte store of eight int16
+template <bool VEC>
+__global__ void audiowrite_kernel(const float *__restrict__ data, int64_t n, const unsigned *__restrict__ rowmax,
+                                  int16_t *__restrict__ out, unsigned long long *__restrict__ clipped) {
+  const int row = blockIdx.y;
+  const float *src = data + static_cast<int64_t>(row) * n;
+  int16_t *dst = out + static_cast<int64_t>(row) * n;
+  const bool norm = rowmax != nullptr;
+  const float peak = norm ? __uint_as_float(rowmax[row]) : 1.f;
+  unsigned over = 0;
+  constexpr int V = VEC ? 8 : 1;
+  for (int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * V; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x * V) {
+    if (VEC) {
+      const float4 a = __ldg(reinterpret_cast<const float4 *>(src + i));
+      const float4 b = __ldg(reinterpret_cast<const float4 *>(src + i) + 1);
+      const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      uint32_t w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t lo = static_cast<uint16_t>(audiowrite_one(v[2 * k], norm, peak, over));
+        const uint32_t hi = static_cast<uint16_t>(audiowrite_one(v[2 * k + 1], norm, peak, over));
+        w[k] = lo | (hi << 16);
+      }
+      *reinterpret_cast<uint4 *>(dst + i) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+      dst[i] = audiowrite_one(__ldg(src + i), norm, peak, over);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) over += __shfl_xor_sync(0xffffffffu, over, o);
+  if ((threadIdx.x & 31) == 0 && over) atomicAdd(clipped + row, static_cast<unsigned long long>(over));
+}
+
+}  // namespace sep
+
+using namespace sep;
+
+extern "C" int sep_pcm16_to_f32(const int16_t *pcm, int64_t n, float *out, int mem, void *stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SEP_REQUIRE(pcm && out && n >= 0, "sep_pcm16_to_f32: bad argument");
+  int rc = check_mem(mem);
+  if (rc) return rc;
+  if (n == 0) return SEP_OK;
+  Scratch s(stream);
+  const int16_t *d_in;
+  float *d_out;
+  if ((rc = stage_in(s, pcm, static_cast<size_t>(n), mem, &d_in))) return rc;
+  if ((rc = stage_out(s, out, static_cast<size_t>(n), mem, &d_out))) return rc;
+  const int64_t threads = (n + 7) / 8;
+  profile_begin(stream);
+  pcm16_to_f32_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(d_in, n, d_out);
+  profile_end(stream);
+  SEP_LAUNCHED();
+  if ((rc = copy_back(s, out, d_out, static_cast<size_t>(n), mem))) return rc;
+  return finish(s, mem);
+}
+
+extern "C" int sep_audiowrite_i16_f32(const float *data, int batch, int64_t n, int normalize, int16_t *out,
+                                      int64_t *clipped, int mem, void *stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SEP_REQUIRE(data && out && batch >= 1 && n >= 1, "sep_audiowrite_i16_f32: bad argument");
+  int rc = check_mem(mem);
+  if (rc) return rc;
+  Scratch s(stream);
+  const size_t count = static_cast<size_t>(batch) * n;
+  const float *d_in;
+  int16_t *d_out;
+  unsigned long long *d_clip;
+  unsigned *d_max = nullptr;
+  if ((rc = stage_in(s, data, count, mem, &d_in))) return rc;
+  if ((rc = stage_out(s, out, count, mem, &d_out))) return rc;
+  if ((rc = s.alloc(&d_clip, static_cast<size_t>(batch)))) return rc;
+  SEP_CUDA(cudaMemsetAsync(d_clip, 0, sizeof(unsigned long long) * batch, stream));
+  const bool vec = n % 8 == 0 && ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
+  // enough CTAs to fill the machine a few times over, whatever the batch
+  const int64_t per_block = 256 * (vec ? 8 : 1) * 4;
+  const unsigned bx = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((n + per_block - 1) / per_block,
+                                                                             (148 * 32 + batch - 1) / batch)));
+  const dim3 grid(bx, batch);
+  profile_begin(stream);
+  if (normalize) {
+    if ((rc = s.alloc(&d_max, static_cast<size_t>(batch)))) return rc;
+    SEP_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned) * batch, stream));
+    if (vec) row_absmax_kernel<true><<<grid, 256, 0, stream>>>(d_in, n, d_max);
+    else row_absmax_kernel<false><<<grid, 256, 0, stream>>>(d_in, n, d_max);
+    SEP_LAUNCHED();
+  }
+  if (vec) audiowrite_kernel<true><<<grid, 256, 0, stream>>>(d_in, n, d_max, d_out, d_clip);
+  else audiowrite_kernel<false><<<grid, 256, 0, stream>>>(d_in, n, d_max, d_out, d_clip);
+  profile_end(stream);
+  SEP_LAUNCHED();
+  if ((rc = copy_back(s, out, d_out, count, mem))) return rc;
+  if (clipped) {
+    static_assert(sizeof(unsigned long long) == sizeof(int64_t), "clipped counter width");
+    if (mem == SEP_MEM_HOST) {
+      SEP_CUDA(cudaMemcpyAsync(clipped, d_clip, sizeof(int64_t) * batch, cudaMemcpyDeviceToHost, stream));
+    } else {
+      SEP_CUDA(cudaMemcpyAsync(clipped, d_clip, sizeof(int64_t) * batch, cudaMemcpyDeviceToDevice, stream));
+    }
+  }
+  return finish(s, mem);
+}

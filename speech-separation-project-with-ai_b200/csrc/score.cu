@@ -190,26 +190,24 @@ static int run_score(const float *d_refs, const float *d_ests, const int64_t *d_
 // Pinned staging for per-call metadata: a small per-thread ring; a slot is reused only after the copy that
 // read it has completed (event), so entry points can stay asynchronous.
 struct MetaSlot { void *host = nullptr; size_t cap = 0; cudaEvent_t copied = nullptr; };
-static MetaSlot *meta_slot(size_t bytes) {
+static int meta_slot(size_t bytes, MetaSlot **out) {
   static thread_local MetaSlot ring[4];
   static thread_local unsigned next = 0;
   MetaSlot &m = ring[next++ % 4];
-  if (m.copied == nullptr) {
-    if (cudaEventCreateWithFlags(&m.copied, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-  } else if (cudaEventSynchronize(m.copied) != cudaSuccess) {
-    return nullptr;
-  }
+  if (m.copied == nullptr) SEP_CUDA(cudaEventCreateWithFlags(&m.copied, cudaEventDisableTiming));
+  else SEP_CUDA(cudaEventSynchronize(m.copied));
   if (m.cap < bytes) {
     if (m.host) cudaFreeHost(m.host);
     m.host = nullptr;
     m.cap = 0;
     if (cudaMallocHost(&m.host, bytes + bytes / 2) != cudaSuccess) {
       set_error("sep_score_batch_f32: cannot allocate %zu bytes of pinned staging memory", bytes);
-      return nullptr;
+      return SEP_ERR_NOMEM;
     }
     m.cap = bytes + bytes / 2;
   }
-  return &m;
+  *out = &m;
+  return SEP_OK;
 }
 
 }  // namespace sep
@@ -234,8 +232,8 @@ extern "C" int sep_score_batch_f32(const float *refs, const float *ests, const i
   // the call never blocks on the stream: [ref_off B*C | est_off B*C | lengths B] int64, [chunk_start B+1] int32.
   const size_t n_off = static_cast<size_t>(batch) * C;
   const size_t meta_bytes = (2 * n_off + batch) * sizeof(int64_t) + (static_cast<size_t>(batch) + 1) * sizeof(int32_t);
-  MetaSlot *slot = meta_slot(meta_bytes);
-  if (!slot) return SEP_ERR_NOMEM;
+  MetaSlot *slot = nullptr;
+  if ((rc = meta_slot(meta_bytes, &slot))) return rc;
   int64_t *h_roff = static_cast<int64_t *>(slot->host), *h_eoff = h_roff + n_off, *h_len = h_eoff + n_off;
   int32_t *start = reinterpret_cast<int32_t *>(h_len + batch);
   start[0] = 0;

@@ -542,3 +542,61 @@ def test_filterbank_unsupported_shape(sep):
     with pytest.raises(NotImplementedError):
         sep.filterbank_separate(np.zeros((1, 400), np.float32), np.zeros((20, 64), np.float32),
                                 np.zeros((64, 20), np.float32), np.zeros((1, 1, 39, 64), np.float32), stride=10)
+
+
+# ----------------------------------------------------------------- 8f rank 3: sample formats
+@pytest.mark.gpu
+def test_audiowrite_and_pcm_bit_exact(sep, oracle):
+    import os
+    import torch
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "audiowrite_golden.npz"))
+    for name in ("quiet", "loud", "edge"):
+        for norm in (0, 1):
+            pcm, clipped = sep.audiowrite_int16(g[name + "_x"], bool(norm))
+            assert np.array_equal(pcm, g["%s_%d_pcm" % (name, norm)]), (name, norm)     # reference cell 40, bit exact
+            assert clipped == int(g["%s_%d_clipped" % (name, norm)])
+    rng = np.random.default_rng(8)
+    x = (0.5 * rng.standard_normal((7, 12345))).astype(np.float32)
+    for norm in (False, True):
+        got, clipped = sep.audiowrite_int16(x, norm)
+        dgot, dclipped = sep.audiowrite_int16(torch.from_numpy(x).cuda(), norm)
+        for b in range(7):
+            want, wc = oracle.audiowrite_int16(x[b], norm)
+            assert np.array_equal(got[b], want) and int(clipped[b]) == wc
+        assert np.array_equal(dgot.cpu().numpy(), got) and np.array_equal(dclipped.cpu().numpy(), clipped)
+    pcm = rng.integers(-32768, 32768, size=100003).astype(np.int16)
+    assert np.array_equal(sep.pcm16_to_float32(pcm), oracle.pcm16_to_float32(pcm))
+    assert np.array_equal(sep.pcm16_to_float32(torch.from_numpy(pcm).cuda()).cpu().numpy(), oracle.pcm16_to_float32(pcm))
+    # wav round trip through the reference-named writer
+    path = "/tmp/sepcore_audiowrite_test.wav"
+    assert sep.audiowrite(x[0], path, 8000, True, False) == 0
+    from scipy.io import wavfile
+    rate, data = wavfile.read(path)
+    assert rate == 8000 and np.array_equal(data, oracle.audiowrite_int16(x[0], True)[0])
+
+
+# ----------------------------------------------------------------- 8f rank 4: TF-style SI-SDR metric / loss
+@pytest.mark.gpu
+def test_tf_style_sisdr_metric_and_loss(sep, oracle):
+    import torch
+    rng = np.random.default_rng(21)
+    y_true = rng.standard_normal((6, 4001, 1)).astype(np.float32)
+    metric, dmetric = sep.SiSdr(), sep.SiSdr()
+    total, count = 0.0, 0
+    for rows in (4000, 3500, 4400):
+        y_pred = rng.standard_normal((6, rows, 1)).astype(np.float32) * 0.3
+        n = min(4000, rows)
+        y_pred[:, :n] += y_true[:, :n]
+        want = oracle.sisdr_values(y_true, y_pred)
+        got = sep.sisdr_values(y_true, y_pred)
+        assert np.max(np.abs(got - want)) < TOL_DB
+        w = rng.random(6).astype(np.float32)
+        metric.update_state(y_true, y_pred, sample_weight=w)
+        dmetric.update_state(torch.from_numpy(y_true).cuda(), torch.from_numpy(y_pred).cuda(), sample_weight=w)
+        total += float(np.sum(want * w))
+        count += 6
+    assert abs(metric.result() - total / count) < TOL_DB and abs(dmetric.result() - total / count) < TOL_DB
+    metric.reset_states()
+    assert metric.count == 0.0
+    y_pred = (y_true[:, :4000] + 0.1 * rng.standard_normal((6, 4000, 1))).astype(np.float32)
+    assert abs(sep.custom_sisdr_loss(y_true, y_pred) - oracle.custom_sisdr_loss(y_true, y_pred)) < TOL_DB
