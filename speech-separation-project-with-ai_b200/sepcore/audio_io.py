@@ -14,15 +14,19 @@ from . import _lib
 from ._buffers import as_f32_host, current_stream, is_device_tensor, ptr
 
 
-def pcm16_to_float32(pcm):
-    """int16 PCM -> float32 in [-1, 1): pcm / 32768 (what sf.read(dtype='float32') returns)."""
+def pcm16_to_float32(pcm, out=None):
+    """int16 PCM -> float32 in [-1, 1): pcm / 32768 (what sf.read(dtype='float32') returns).
+    `out` (device mode): a preallocated contiguous float32 CUDA tensor of the same shape."""
     lib = _lib.load()
     if is_device_tensor(pcm):
         import torch
 
         if pcm.dtype != torch.int16 or not pcm.is_contiguous():
             raise ValueError("pcm must be a contiguous int16 CUDA tensor")
-        out = torch.empty(pcm.shape, dtype=torch.float32, device=pcm.device)
+        if out is None:
+            out = torch.empty(pcm.shape, dtype=torch.float32, device=pcm.device)
+        elif out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != pcm.numel():
+            raise ValueError("out must be a contiguous float32 CUDA tensor with pcm's element count")
         mem, n, stream = _lib.MEM_DEVICE, pcm.numel(), current_stream(_lib.MEM_DEVICE, pcm)
     else:
         pcm = np.ascontiguousarray(pcm, dtype=np.int16)
@@ -32,9 +36,10 @@ def pcm16_to_float32(pcm):
     return out
 
 
-def audiowrite_int16(data, normalize=False):
+def audiowrite_int16(data, normalize=False, out=None, clipped=None):
     """The sample conversion inside `audiowrite` (cell 40 :1331-1346) for float32 data [n] or [B, n]
-    (row by row): returns (int16 array, clipped count per row -- a Python int for 1-D input)."""
+    (row by row): returns (int16 array, clipped count per row -- a Python int for 1-D input).
+    `out` / `clipped` (device mode): preallocated int16 [B, n] / int64 [B] CUDA tensors."""
     lib = _lib.load()
     dev = is_device_tensor(data)
     if dev:
@@ -42,8 +47,10 @@ def audiowrite_int16(data, normalize=False):
 
         x = data if data.dtype == torch.float32 and data.is_contiguous() else data.float().contiguous()
         rows = x.reshape(1, -1) if x.dim() == 1 else x
-        out = torch.empty(rows.shape, dtype=torch.int16, device=x.device)
-        clipped = torch.empty((rows.shape[0],), dtype=torch.int64, device=x.device)
+        if out is None:
+            out = torch.empty(rows.shape, dtype=torch.int16, device=x.device)
+        if clipped is None:
+            clipped = torch.empty((rows.shape[0],), dtype=torch.int64, device=x.device)
         mem, stream = _lib.MEM_DEVICE, current_stream(_lib.MEM_DEVICE, x)
     else:
         x = as_f32_host(data)

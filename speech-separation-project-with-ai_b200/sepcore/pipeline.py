@@ -23,16 +23,21 @@ class HostPipeline:
     arrays (views of pinned host memory owned by the slot, valid until the slot is
     reused `depth` submits later).  Inputs may be numpy arrays or CPU tensors;
     pinned inputs are copied asynchronously, pageable ones synchronously (CUDA rule).
+
+    pcm16=True: the waveforms cross PCIe in the format they have on disk -- mixture and references
+    as int16 PCM (decoded on the device exactly like wavread / librosa.load do: x / 32768), the
+    estimates as the int16 samples `audiowrite(wav, path, rate, normalize=True)` would write
+    (uPIT_baseline.ipynb:1403-1404), plus the per-row clipped counts: half the waveform bytes each way.
     """
 
     def __init__(self, batch, n_src, n_samples, size=256, shift=128, window=None, depth=3,
-                 scored=True, want_est=True, device=None):
+                 scored=True, want_est=True, device=None, pcm16=False):
         import torch
 
         self.torch = torch
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
         self.kw = dict(size=size, shift=shift, window=window, want_est=want_est)
-        self.scored, self.want_est, self.depth = scored, want_est, int(depth)
+        self.scored, self.want_est, self.depth, self.pcm16 = scored, want_est, int(depth), bool(pcm16)
         from .plan import get_plan
 
         plan = get_plan(size, shift, window, True)
@@ -52,9 +57,19 @@ class HostPipeline:
                 "ev_in": torch.cuda.Event(), "ev_done": torch.cuda.Event(), "ev_out": torch.cuda.Event(),
                 "busy": False,
             }
+            if self.pcm16:
+                i16 = dict(dtype=torch.int16, device=self.dev)
+                s["mix_i16"] = torch.empty((batch, n_samples), **i16)
+                s["refs_i16"] = torch.empty((batch, n_src, n_samples), **i16) if scored else None
             if want_est:
                 s["out"]["est"] = torch.empty((batch, n_src, n_samples), **f32)
-                s["host"]["est"] = torch.empty((batch, n_src, n_samples), dtype=torch.float32).pin_memory()
+                if self.pcm16:
+                    s["est_i16"] = torch.empty((batch * n_src, n_samples), dtype=torch.int16, device=self.dev)
+                    s["clipped"] = torch.empty((batch * n_src,), dtype=torch.int64, device=self.dev)
+                    s["host"]["est"] = torch.empty((batch, n_src, n_samples), dtype=torch.int16).pin_memory()
+                    s["host"]["clipped"] = torch.empty((batch, n_src), dtype=torch.int64).pin_memory()
+                else:
+                    s["host"]["est"] = torch.empty((batch, n_src, n_samples), dtype=torch.float32).pin_memory()
             if scored:
                 s["out"]["scores"] = torch.empty((batch, stride), dtype=torch.float64, device=self.dev)
                 s["out"]["sums"] = torch.empty((4,), dtype=torch.float64, device=self.dev)
@@ -65,8 +80,9 @@ class HostPipeline:
         self.s_run = torch.cuda.Stream(device=self.dev)
         self.s_out = torch.cuda.Stream(device=self.dev)
         self.count = 0
-        self.h2d_bytes = sum(s["mix"].numel() * 4 for s in self.slots[:1]) \
-            + self.slots[0]["masks"].numel() * 4 + (self.slots[0]["refs"].numel() * 4 if scored else 0)
+        wave_bytes = 2 if self.pcm16 else 4
+        self.h2d_bytes = self.slots[0]["mix"].numel() * wave_bytes + self.slots[0]["masks"].numel() * 4 \
+            + (self.slots[0]["refs"].numel() * wave_bytes if scored else 0)
         self.d2h_bytes = sum(v.numel() * v.element_size() for v in self.slots[0]["host"].values())
 
     def _as_tensor(self, x):
@@ -80,21 +96,35 @@ class HostPipeline:
             slot["ev_out"].synchronize()          # the slot's previous results have reached the host
         slot["busy"] = True
         with torch.cuda.stream(self.s_in):
-            slot["mix"].copy_(self._as_tensor(mix), non_blocking=True)
+            slot["mix_i16" if self.pcm16 else "mix"].copy_(self._as_tensor(mix), non_blocking=True)
             slot["masks"].copy_(self._as_tensor(masks), non_blocking=True)
             if self.scored:
-                slot["refs"].copy_(self._as_tensor(refs), non_blocking=True)
+                slot["refs_i16" if self.pcm16 else "refs"].copy_(self._as_tensor(refs), non_blocking=True)
             slot["ev_in"].record(self.s_in)
         with torch.cuda.stream(self.s_run):
             self.s_run.wait_event(slot["ev_in"])
+            if self.pcm16:
+                from . import audio_io
+
+                audio_io.pcm16_to_float32(slot["mix_i16"], out=slot["mix"])
+                if self.scored:
+                    audio_io.pcm16_to_float32(slot["refs_i16"], out=slot["refs"])
             out = dict(slot["out"])
             fused.separate_and_score(slot["mix"], slot["masks"], slot["refs"], out=out,
                                      workspace=slot["workspace"], **self.kw)
+            if self.pcm16 and self.want_est:
+                audio_io.audiowrite_int16(slot["out"]["est"].reshape(slot["est_i16"].shape), True,
+                                          out=slot["est_i16"], clipped=slot["clipped"])
             slot["ev_done"].record(self.s_run)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(slot["ev_done"])
             for key, host in slot["host"].items():
-                host.copy_(slot["out"][key], non_blocking=True)
+                if self.pcm16 and key == "est":
+                    host.copy_(slot["est_i16"].reshape(host.shape), non_blocking=True)
+                elif key == "clipped":
+                    host.copy_(slot["clipped"].reshape(host.shape), non_blocking=True)
+                else:
+                    host.copy_(slot["out"][key], non_blocking=True)
             slot["ev_out"].record(self.s_out)
         self.count += 1
         return ticket
@@ -108,6 +138,8 @@ class HostPipeline:
         res = {}
         if self.want_est:
             res["est"] = slot["host"]["est"].numpy()
+            if self.pcm16:
+                res["clipped"] = slot["host"]["clipped"].numpy()
         if self.scored:
             scores = slot["host"]["scores"].numpy()
             res.update(fused.parse_scores(scores, self.n_src))

@@ -600,3 +600,27 @@ def test_tf_style_sisdr_metric_and_loss(sep, oracle):
     assert metric.count == 0.0
     y_pred = (y_true[:, :4000] + 0.1 * rng.standard_normal((6, 4000, 1))).astype(np.float32)
     assert abs(sep.custom_sisdr_loss(y_true, y_pred) - oracle.custom_sisdr_loss(y_true, y_pred)) < TOL_DB
+
+
+@pytest.mark.gpu
+def test_host_pipeline_pcm16(sep, oracle):
+    """HostPipeline(pcm16=True): int16 waveforms in, audiowrite(normalize=True) int16 estimates out --
+    the same numbers as decoding on the host, running the float32 pipeline and converting with the oracle."""
+    import torch
+    rng = np.random.default_rng(31)
+    cfg = CONFIGS["blackman_256_128"]
+    batch, n_src, n = 5, 2, 8000
+    mix, refs, masks, _ = _fused_case(rng, batch, n, n_src, cfg, oracle)
+    mix16 = np.round(np.clip(mix, -1, 1) * 32767).astype(np.int16)
+    refs16 = np.round(np.clip(refs, -1, 1) * 32767).astype(np.int16)
+    pipe = sep.HostPipeline(batch, n_src, n, depth=2, pcm16=True, **cfg)
+    t = pipe.submit(torch.from_numpy(mix16).pin_memory(), torch.from_numpy(masks).pin_memory(),
+                    torch.from_numpy(refs16).pin_memory())
+    got = pipe.result(t)
+    want = sep.separate_and_score(oracle.pcm16_to_float32(mix16), masks, oracle.pcm16_to_float32(refs16), **cfg)
+    assert np.array_equal(got["scores"], want["scores"])
+    for b in range(batch):
+        for c in range(n_src):
+            pcm, clipped = oracle.audiowrite_int16(want["est"][b, c], True)
+            assert np.array_equal(got["est"][b, c], pcm) and int(got["clipped"][b, c]) == clipped
+    assert pipe.h2d_bytes == mix16.nbytes + refs16.nbytes + masks.nbytes
