@@ -410,15 +410,22 @@ def run_sepcore(args):
                                  "streams inside the graph)" % (block, graph.n_streams),
                        "parallelism": "utterance-sharded x%d, all-reduce of per-batch sums bucketed per replay"
                                       % world},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "dominant fused kernel (strip256_kernel at 256/{128,64}, C<=2) (timed alone, one launch at a time, CUDA events "
-                                   "around the launch on its stream)",
-                         "kernel_ms": kernel_ms_avg, "bytes_per_launch": bytes_per_launch,
-                         "launches_timed": bracketed,
-                         # the same bytes over the overlapped step time of the graph-replayed loop
-                         "achieved_in_loop": bytes_per_launch / (ms_total / args.steps * 1e-3) / 1e9,
-                         "frac_in_loop": bytes_per_launch / (ms_total / args.steps * 1e-3) / 1e9 / peak},
+            # The timed region is the graph-replayed loop: one launch of the dominant kernel per step, steps of
+            # different streams overlapping (its CTAs move in as the previous launch's retire), the two small
+            # finalisation kernels hidden underneath.  achieved = algorithmic bytes per launch / (timed region /
+            # launches).  "alone" is the same kernel launched eagerly, one at a time, events around the launch.
+            "roofline": {"bound": "hbm", "achieved": bytes_per_launch / (ms_total / args.steps * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s",
+                         "frac": bytes_per_launch / (ms_total / args.steps * 1e-3) / 1e9 / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "strip256_kernel (256/{128,64}, C<=2) / strip512_kernel (512/128) / tile or generic "
+                                   "kernel otherwise; CUDA events around the timed region on the launching stream",
+                         "kernel_ms": ms_total / args.steps, "bytes_per_launch": bytes_per_launch,
+                         "launches_timed": args.steps,
+                         "alone": {"kernel_ms": kernel_ms_avg, "achieved": achieved, "frac": achieved / peak,
+                                   "launches_timed": bracketed,
+                                   "how": "eager launches, one at a time, CUDA events around each launch on its stream "
+                                          "(includes ~4 us of launch / event overhead; ncu: see profiles/)"}},
             "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps * world),
             "clocks": clocks, "check": {"pit_loss_sum": sums[0], "si_sdr_sum": sums[1], "n": sums[3]},
         }

@@ -18,6 +18,7 @@
 // mask multiply, the next references after the Gram statistics.
 // Reference lines: see fused.cu.
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "fft256.cuh"
@@ -190,60 +191,68 @@ __global__ void __launch_bounds__(W * 32, 8 / W) strip512_kernel(const FusedArgs
 #pragma unroll
         for (int i = 0; i < C; ++i) pj[i] = 0.f;
         const bool anyzero = sg > 0 && __any_sync(0xffffffffu, !(pmin > 0.f));
+        // one straight-line body per case (mixture / labels / labels with exactly-zero mixture bins): the case is
+        // decided once per transform, not per bin
+        auto bins = [&](auto mix_tag, auto zero_tag) {
+          constexpr bool MIX = decltype(mix_tag)::value, ZERO = decltype(zero_tag)::value;
 #pragma unroll
-        for (int r = 0; r < 16; r += 2) {
-          const float4 w4 = tw5[r / 2];
+          for (int r = 0; r < 16; r += 2) {
+            const float4 w4 = tw5[r / 2];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int rr = r + h;
-            const float2 wk = h == 0 ? make_float2(w4.x, w4.y) : make_float2(w4.z, w4.w);
-            float2 got;
-            got.x = __shfl_sync(0xffffffffu, v[15 - rr].x, src_lane, 16);
-            got.y = __shfl_sync(0xffffffffu, v[15 - rr].y, src_lane, 16);
-            const float2 own = v[(16 - rr) & 15];
-            const float2 zp = l16 == 0 ? own : got;
-            const float2 z = v[rr];
-            const float2 E = cadd_conj(z, zp);                                        // Z + conj Z'
-            const float2 O = __fadd2_rn(z, make_float2(-zp.x, zp.y));                 // Z - conj Z'
-            const float2 Gk = cmul(O, make_float2(-wk.y, wk.x));                      // i W^k O
-            const float2 Sx = csub(E, Gk);
-            if (sg == 0) {
-              X[rr] = Sx;
-              if (rr == 0) X[16] = cadd(E, Gk);
-              if (SCORE) {
-                const float p = fmaf(Sx.x, Sx.x, Sx.y * Sx.y);
-                pmin = fminf(pmin, p);
-                inv[rr] = rsqrt_fast(fmaxf(p, 1e-36f));
-                mag[rr] = p * inv[rr] * gate;
-                if (rr == 0) {
-                  const float p16 = fmaf(X[16].x, X[16].x, X[16].y * X[16].y);
-                  pmin = fminf(pmin, l16 == 0 ? p16 : 1.f);
-                  inv[16] = rsqrt_fast(fmaxf(p16, 1e-36f));
-                  mag[16] = p16 * inv[16] * gate;
+            for (int h = 0; h < 2; ++h) {
+              const int rr = r + h;
+              const float2 wk = h == 0 ? make_float2(w4.x, w4.y) : make_float2(w4.z, w4.w);
+              float2 got;
+              got.x = __shfl_sync(0xffffffffu, v[15 - rr].x, src_lane, 16);
+              got.y = __shfl_sync(0xffffffffu, v[15 - rr].y, src_lane, 16);
+              const float2 own = v[(16 - rr) & 15];
+              const float2 zp = l16 == 0 ? own : got;
+              const float2 z = v[rr];
+              const float2 E = cadd_conj(z, zp);                                        // Z + conj Z'
+              const float2 O = __fadd2_rn(z, make_float2(-zp.x, zp.y));                 // Z - conj Z'
+              const float2 Gk = cmul(O, make_float2(-wk.y, wk.x));                      // i W^k O
+              const float2 Sx = csub(E, Gk);
+              if (MIX) {
+                X[rr] = Sx;
+                if (rr == 0) X[16] = cadd(E, Gk);
+                if (SCORE) {
+                  const float p = fmaf(Sx.x, Sx.x, Sx.y * Sx.y);
+                  pmin = fminf(pmin, p);
+                  inv[rr] = rsqrt_fast(fmaxf(p, 1e-36f));
+                  mag[rr] = p * inv[rr] * gate;
+                  if (rr == 0) {
+                    const float p16 = fmaf(X[16].x, X[16].x, X[16].y * X[16].y);
+                    pmin = fminf(pmin, l16 == 0 ? p16 : 1.f);
+                    inv[16] = rsqrt_fast(fmaxf(p16, 1e-36f));
+                    mag[16] = p16 * inv[16] * gate;
+                  }
                 }
-              }
-            } else {
-              // label = |S| cos(angle X - angle S) = Re(S conj X) / |X| ; angle(0) = 0 -> Re S
-              float l = fmaf(Sx.x, X[rr].x, Sx.y * X[rr].y) * inv[rr];
-              if (anyzero && !(fmaf(X[rr].x, X[rr].x, X[rr].y * X[rr].y) > 0.f)) l = Sx.x;
-#pragma unroll
-              for (int i = 0; i < C; ++i) {
-                const float d = fmaf(mrow[i * MROW + l16 + 16 * rr], mag[rr], -l);
-                pj[i] = fmaf(d, d, pj[i]);
-              }
-              if (rr == 0) {
-                const float2 S16 = cadd(E, Gk);
-                float l16v = fmaf(S16.x, X[16].x, S16.y * X[16].y) * inv[16];
-                if (anyzero && !(fmaf(X[16].x, X[16].x, X[16].y * X[16].y) > 0.f)) l16v = S16.x;
+              } else {
+                // label = |S| cos(angle X - angle S) = Re(S conj X) / |X| ; angle(0) = 0 -> Re S
+                float l = fmaf(Sx.x, X[rr].x, Sx.y * X[rr].y) * inv[rr];
+                if (ZERO && !(fmaf(X[rr].x, X[rr].x, X[rr].y * X[rr].y) > 0.f)) l = Sx.x;
 #pragma unroll
                 for (int i = 0; i < C; ++i) {
-                  const float d = fmaf(mrow[i * MROW + 256], mag[16], -l16v) * bw16;
+                  const float d = fmaf(mrow[i * MROW + l16 + 16 * rr], mag[rr], -l);
                   pj[i] = fmaf(d, d, pj[i]);
+                }
+                if (rr == 0) {
+                  const float2 S16 = cadd(E, Gk);
+                  float l16v = fmaf(S16.x, X[16].x, S16.y * X[16].y) * inv[16];
+                  if (ZERO && !(fmaf(X[16].x, X[16].x, X[16].y * X[16].y) > 0.f)) l16v = S16.x;
+#pragma unroll
+                  for (int i = 0; i < C; ++i) {
+                    const float d = fmaf(mrow[i * MROW + 256], mag[16], -l16v) * bw16;
+                    pj[i] = fmaf(d, d, pj[i]);
+                  }
                 }
               }
             }
           }
-        }
+        };
+        if (sg == 0) bins(std::true_type{}, std::false_type{});
+        else if (!anyzero) bins(std::false_type{}, std::false_type{});
+        else bins(std::false_type{}, std::true_type{});
         if (sg > 0) {
           // fold into column j = sg - 1 without indexing registers by a runtime value
 #pragma unroll
