@@ -24,6 +24,7 @@
 // is written by exactly one lane, once).  Reference lines: see fused.cu.
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "fft256.cuh"
@@ -224,23 +225,28 @@ __global__ void __launch_bounds__(W * 32, 8 / W) strip256_kernel(const FusedArgs
 #pragma unroll
           for (int i = 0; i < C; ++i) pj[i] = make_float2(0.f, 0.f);
           const bool anyzero = __any_sync(0xffffffffu, !(pmin > 0.f));
+          // one straight-line bin loop per case (ordinary / some mixture bin exactly zero)
+          auto bins = [&](auto zero_tag) {
+            constexpr bool ZERO = decltype(zero_tag)::value;
 #pragma unroll
-          for (int r = 0; r < 9; ++r) {
-            float2 SR, SI;
-            split_planar(v, l16, r, SR, SI);
-            float2 l = __fmul2_rn(__ffma2_rn(SR, XR[r], __fmul2_rn(SI, XI[r])), inv[r]);
-            if (anyzero) {
-              const float2 p = __ffma2_rn(XR[r], XR[r], __fmul2_rn(XI[r], XI[r]));
-              if (!(p.x > 0.f)) l.x = SR.x;
-              if (!(p.y > 0.f)) l.y = SR.y;
-            }
+            for (int r = 0; r < 9; ++r) {
+              float2 SR, SI;
+              split_planar(v, l16, r, SR, SI);
+              float2 l = __fmul2_rn(__ffma2_rn(SR, XR[r], __fmul2_rn(SI, XI[r])), inv[r]);
+              if (ZERO) {
+                const float2 p = __ffma2_rn(XR[r], XR[r], __fmul2_rn(XI[r], XI[r]));
+                if (!(p.x > 0.f)) l.x = SR.x;
+                if (!(p.y > 0.f)) l.y = SR.y;
+              }
 #pragma unroll
-            for (int i = 0; i < C; ++i) {
-              float2 d = __ffma2_rn(mab[i][r], mag[r], make_float2(-l.x, -l.y));
-              if (r == 8) d = __fmul2_rn(d, make_float2(bw8, bw8));
-              pj[i] = __ffma2_rn(d, d, pj[i]);
+              for (int i = 0; i < C; ++i) {
+                float2 d = __ffma2_rn(mab[i][r], mag[r], make_float2(-l.x, -l.y));
+                if (r == 8) d = __fmul2_rn(d, make_float2(bw8, bw8));
+                pj[i] = __ffma2_rn(d, d, pj[i]);
+              }
             }
-          }
+          };
+          if (!anyzero) bins(std::false_type{}); else bins(std::true_type{});
           // fold into column j = sg - 1 without indexing registers by a runtime value
 #pragma unroll
           for (int jj = 0; jj < C; ++jj) {
