@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(W * 32, 8 / W) strip256_kernel(const FusedArgs
       // one path per warp: if either half-warp has an edge, both take the predicated path (instead of the
       // two paths running one after the other)
       const bool plain = !__any_sync(0xffffffffu, !(skip == 0 && lim_v == NOUT));
-#pragma unroll 1
+#pragma unroll
       for (int q = 0; q < C; ++q) {
         {
           float2 L[9], Mi[9];
