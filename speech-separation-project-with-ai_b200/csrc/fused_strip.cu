@@ -50,9 +50,10 @@ struct StripGeom {
   __host__ __device__ static constexpr int sk(int i) { return i + 16 * (i / (2 * SHIFT)); }
   static constexpr int SPAN_SK = (sk(SPAN - 1) + 1 + 3) & ~3;
   static constexpr int UNIT_STRIDE = C * NSLOT * 16 + 16;      // == 16 (mod 32): half-warps on disjoint banks
-  // the mixture span is double-buffered (fetched one iteration ahead); the reference spans are
-  // single-buffered: requested at the top of an iteration, needed only after the mixture transform
-  static constexpr int STAGE_FLOATS = (2 + (NSIG - 1)) * SPAN_SK;
+  // every span is single-buffered but requested as early as its buffer is free: the next mixture span right
+  // after this one has been read into registers, the reference spans at the top of their iteration (needed
+  // only after the mixture transform)
+  static constexpr int STAGE_FLOATS = NSIG * SPAN_SK;
   // tail slots: [unit 0] and [unit 1][parity] for R = 2 (only unit 1's tail crosses an iteration);
   // [parity][unit] for R = 4 (a frame pair also needs its own tail of the previous iteration)
   static constexpr int NSLOTBUF = (R == 2) ? 3 : 4;
@@ -62,8 +63,8 @@ struct StripGeom {
   static constexpr int NV = FusedVals<C>::NV;
 };
 
-template <int C, int R, bool SCORE, int W>
-__global__ void __launch_bounds__(W * 32, 8 / W) strip256_kernel(const FusedArgs a) {
+template <int C, int R, bool SCORE, int W, int CPS>
+__global__ void __launch_bounds__(W * 32, CPS) strip256_kernel(const FusedArgs a) {
   using G = StripGeom<C, R, SCORE, W>;
   constexpr int SHIFT = G::SHIFT, H = G::H, NSIG = G::NSIG, D = G::D, NY = G::NY, NOUT = G::NOUT;
   constexpr int NSLOT = G::NSLOT, SPAN = G::SPAN, SSK = G::SPAN_SK, US = G::UNIT_STRIDE, NV = G::NV;
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(W * 32, 8 / W) strip256_kernel(const FusedArgs
 #pragma unroll
         for (int sg = 0; sg < NSIG; ++sg) {
           if (sg < sig_lo || sg >= sig_hi) continue;
-          float *dst = (sg == 0 ? stage + (it & 1) * SSK : stage + (1 + sg) * SSK) + 4 * lane;
+          float *dst = stage + sg * SSK + 4 * lane;
           const float *src = (sg == 0 ? mix_row : ref_row + static_cast<int64_t>(sg - 1) * a.n) + g0 + 4 * lane;
 #pragma unroll
           for (int c0 = 0; c0 < SPAN / 4; c0 += 32)
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(W * 32, 8 / W) strip256_kernel(const FusedArgs
 #pragma unroll 1
         for (int sg = sig_lo; sg < sig_hi; ++sg) {
           const float *row = sg == 0 ? mix_row : ref_row + static_cast<int64_t>(sg - 1) * a.n;
-          float *dst = sg == 0 ? stage + (it & 1) * SSK : stage + (1 + sg) * SSK;
+          float *dst = stage + sg * SSK;
           if (a.vec_ok) {
             for (int c = lane; c < SPAN / 4; c += 32) {
               const int64_t g = g0 + 4 * c;
@@ -181,8 +182,7 @@ __global__ void __launch_bounds__(W * 32, 8 / W) strip256_kernel(const FusedArgs
       const int ta = a0 + 4 * it + 2 * unit, tb = ta + 1;           // this half-warp's frame pair
       __syncwarp();                                                 // reads of the buffer refilled below are done
       if (NSIG > 1) issue_span(it, 1, NSIG);                        // references of this iteration
-      if (it + 1 < n_it) issue_span(it + 1, 0, 1); else cp_async_commit();   // mixture of the next one
-      if (NSIG > 1) cp_async_wait<2>(); else cp_async_wait<1>();    // this iteration's mixture has landed
+      if (NSIG > 1) cp_async_wait<1>(); else cp_async_wait<0>();    // this iteration's mixture (requested an iteration ago) has landed
       __syncwarp();
       const float *st = stage + ubase;                              // signal sg at st + sig_off(sg)
 
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(W * 32, 8 / W) strip256_kernel(const FusedArgs
       const float2 gate2 = make_float2(ta < len_i ? 1.f : 0.f, tb < len_i ? 1.f : 0.f);
 #pragma unroll 1
       for (int sg = 0; sg < NSIG; ++sg) {
-        const float *sp = st + (sg == 0 ? par * SSK : (1 + sg) * SSK);
+        const float *sp = st + sg * SSK;
         if (sg == 1) {                                              // the references have landed
           cp_async_wait<1>();
           __syncwarp();
@@ -205,6 +205,10 @@ __global__ void __launch_bounds__(W * 32, 8 / W) strip256_kernel(const FusedArgs
           const float2 w = winp[m / 2];
           v[m] = cscale(make_float2(sp[SEP_POS(m)], sp[SEP_POS(m + D)]), w.x);
           v[m + 1] = cscale(make_float2(sp[SEP_POS(m + 1)], sp[SEP_POS(m + 1 + D)]), w.y);
+        }
+        if (sg == 0) {                                              // the mixture span is in registers: refill it
+          __syncwarp();
+          if (it + 1 < n_it) issue_span(it + 1, 0, 1); else cp_async_commit();
         }
         fft256v<false>(v, twl, xch, l16);
         if (sg == 0) {
@@ -331,7 +335,7 @@ __global__ void __launch_bounds__(W * 32, 8 / W) strip256_kernel(const FusedArgs
               eq = fma(e, e, eq);
 #pragma unroll
               for (int j = 0; j < C; ++j) {
-                const double r = static_cast<double>(st[(2 + j) * SSK + SEP_POS(mm)]);
+                const double r = static_cast<double>(st[(1 + j) * SSK + SEP_POS(mm)]);
                 gq[j] = fma(e, r, gq[j]);
                 if (q == 0) rq[j] = fma(r, r, rq[j]);
               }
@@ -348,7 +352,7 @@ __global__ void __launch_bounds__(W * 32, 8 / W) strip256_kernel(const FusedArgs
               eq = fma(e, e, eq);
 #pragma unroll
               for (int j = 0; j < C; ++j) {
-                const double r = okv ? static_cast<double>(st[(2 + j) * SSK + SEP_POS(mm)]) : 0.0;
+                const double r = okv ? static_cast<double>(st[(1 + j) * SSK + SEP_POS(mm)]) : 0.0;
                 gq[j] = fma(e, r, gq[j]);
                 if (q == 0) rq[j] = fma(r, r, rq[j]);
               }
@@ -394,13 +398,12 @@ __global__ void __launch_bounds__(W * 32, 8 / W) strip256_kernel(const FusedArgs
 #undef SEP_POS
 }
 
-template <int C, int R, bool SCORE, int W>
+template <int C, int R, bool SCORE, int W, int CTAS_PER_SM>
 static int launch_strip_w(const sep_plan *p, FusedArgs a, int batch, double *d_scores, double *d_sums,
                           Scratch &s, cudaStream_t stream) {
   using G = StripGeom<C, R, SCORE, W>;
   const int sms = p->sm_count > 0 ? p->sm_count : 148;
-  constexpr int CTAS_PER_SM = 8 / W;                // 8 warps per SM either way
-  pick_strips(a.T, G::H, 4, batch, sms * 8, &a.tiles, &a.strip_iters);
+  pick_strips(a.T, G::H, 4, batch, sms * W * CTAS_PER_SM, &a.tiles, &a.strip_iters);
   int rc;
   double *partials = nullptr;
   int *counters = nullptr;
@@ -420,12 +423,12 @@ static int launch_strip_w(const sep_plan *p, FusedArgs a, int batch, double *d_s
   const auto aligned = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   a.vec_ok = (a.n % 4 == 0) && aligned(a.mix) && (!a.refs || aligned(a.refs)) ? 1 : 0;
   const size_t smem = G::smem();
-  SEP_CUDA(cudaFuncSetAttribute(strip256_kernel<C, R, SCORE, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  SEP_CUDA(cudaFuncSetAttribute(strip256_kernel<C, R, SCORE, W, CTAS_PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
   const int64_t total = static_cast<int64_t>(batch) * a.tiles;
   const int grid = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(sms) * CTAS_PER_SM, (total + W - 1) / W));
   profile_begin(stream);
-  strip256_kernel<C, R, SCORE, W><<<grid, W * 32, smem, stream>>>(a);
+  strip256_kernel<C, R, SCORE, W, CTAS_PER_SM><<<grid, W * 32, smem, stream>>>(a);
   profile_end(stream);
   SEP_LAUNCHED();
   if (SCORE && counters == nullptr) return launch_fused_finalize<C>(a, batch, d_scores, d_sums, stream);
@@ -438,13 +441,8 @@ static int launch_strip(const sep_plan *p, const FusedArgs &a, int batch, double
   // 12 warps (168 registers) were measured slower: the spills miss the small L1 left beside 200 KB of shared memory
   // two 4-warp CTAs per SM (104 KB each) instead of one 8-warp CTA: CTAs of the NEXT launch (another stream
   // of the replayed graph) move in as soon as four warps are done, not eight
-  static const int warps = [] { const char *e = getenv("SEPCORE_STRIP_WARPS"); return e ? atoi(e) : 4; }();
-  switch (warps) {
-    case 1: return launch_strip_w<C, R, SCORE, 1>(p, a, batch, d_scores, d_sums, s, stream);
-    case 2: return launch_strip_w<C, R, SCORE, 2>(p, a, batch, d_scores, d_sums, s, stream);
-    case 8: return launch_strip_w<C, R, SCORE, 8>(p, a, batch, d_scores, d_sums, s, stream);
-    default: return launch_strip_w<C, R, SCORE, 4>(p, a, batch, d_scores, d_sums, s, stream);
-  }
+  // (three CTAs per SM -- 168 registers, 200 bytes of spills per thread -- were measured 40 % slower)
+  return launch_strip_w<C, R, SCORE, 4, 2>(p, a, batch, d_scores, d_sums, s, stream);
 }
 
 template <int C>

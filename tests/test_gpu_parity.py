@@ -356,7 +356,8 @@ def test_fused_strip_edges(sep, oracle, key, n_src, n, batch):
     valid[0] = n
     res = sep.separate_and_score(mix, masks, refs, frame_lengths=lengths, valid_samples=valid, **cfg)
     only = sep.separate_and_score(mix, masks, None, **cfg)
-    assert np.array_equal(only["est"], res["est"])                # same estimates with and without scoring
+    # same estimates with and without scoring (two kernel instantiations: equal up to the last bit or two)
+    assert np.max(np.abs(only["est"] - res["est"])) <= 4e-7 * np.max(np.abs(res["est"]))
     for b in list(range(min(batch, 3))) + [batch - 1]:
         want = oracle.separate_and_score(mix[b], refs[b], masks[b], length=lengths[b], **cfg)
         assert rel_err(res["est"][b], want["ests"][:, :n]) < TOL_REL
