@@ -152,6 +152,8 @@ static int launch_fused_finalize(const FusedArgs &a, int batch, double *d_scores
 
 // Register-resident 256/512-point specialisation (fused_fast.cu).  Sets *handled when it
 // launched; otherwise the generic kernel runs.
+int fused_wstrip_try(const sep_plan *p, const FusedArgs &a, int batch, int C, double *d_scores,
+                     double *d_sums, Scratch &s, cudaStream_t stream, bool *handled);
 int fused_strip_try(const sep_plan *p, const FusedArgs &a, int batch, int C, double *d_scores,
                     double *d_sums, Scratch &s, cudaStream_t stream, bool *handled);
 int fused_strip512_try(const sep_plan *p, const FusedArgs &a, int batch, int C, double *d_scores,

@@ -441,7 +441,8 @@ static int launch_strip(const sep_plan *p, const FusedArgs &a, int batch, double
   // 12 warps (168 registers) were measured slower: the spills miss the small L1 left beside 200 KB of shared memory
   // two 4-warp CTAs per SM (104 KB each) instead of one 8-warp CTA: CTAs of the NEXT launch (another stream
   // of the replayed graph) move in as soon as four warps are done, not eight
-  // (three CTAs per SM -- 168 registers, 200 bytes of spills per thread -- were measured 40 % slower)
+  // (three CTAs per SM -- 168 registers, 200 bytes of spills per thread -- were measured 40 % slower; 10 or 11
+  // warps per SM do not help either: warps are allocated in fours, so ptxas is held to 168 registers all the same)
   return launch_strip_w<C, R, SCORE, 4, 2>(p, a, batch, d_scores, d_sums, s, stream);
 }
 

@@ -378,6 +378,31 @@ def test_fused_strip_edges(sep, oracle, key, n_src, n, batch):
     assert int(res2["pit_perm"][0]) == int(want2["pit"]["idx"][0])
 
 
+@pytest.mark.parametrize("key,n,batch", [("blackman_256_128", 32000, 8), ("hann_256_64", 6001, 5)])
+def test_fused_two_strip_kernels_agree(sep, oracle, monkeypatch, key, n, batch):
+    """Two sources at size 256 run the whole-warp strips (fused_wstrip.cu); SEPCORE_FORCE_HALFWARP=1 sends the
+    same call through the half-warp strips (fused_strip.cu).  Two independent kernels (different FFT
+    factorisation, different strip partition): same estimates up to float32 round-off, identical permutations,
+    scores inside the contract -- and the half-warp kernel stays covered against the oracle."""
+    cfg = CONFIGS[key]
+    rng = np.random.default_rng(11 + n)
+    mix, refs, masks, lengths = _fused_case(rng, batch, n, 2, cfg, oracle, ragged=True)
+    new = sep.separate_and_score(mix, masks, refs, frame_lengths=lengths, **cfg)
+    monkeypatch.setenv("SEPCORE_FORCE_HALFWARP", "1")
+    old = sep.separate_and_score(mix, masks, refs, frame_lengths=lengths, **cfg)
+    monkeypatch.delenv("SEPCORE_FORCE_HALFWARP")
+    assert rel_l2(new["est"], old["est"]) < 2e-6
+    assert np.array_equal(new["pit_perm"], old["pit_perm"])
+    assert np.array_equal(new["si_perm"], old["si_perm"])
+    assert np.allclose(new["pit_pair"], old["pit_pair"], rtol=1e-5)
+    assert np.max(np.abs(new["si_pair"] - old["si_pair"])) < TOL_DB
+    want = oracle.separate_and_score(mix[0], refs[0], masks[0], length=lengths[0], **cfg)
+    for res in (new, old):
+        assert rel_err(res["est"][0], want["ests"][:, :n]) < TOL_REL
+        assert int(res["pit_perm"][0]) == int(want["pit"]["idx"][0])
+        assert np.allclose(res["pit_pair"][0], want["pit"]["pair"][0], rtol=1e-4)
+
+
 def test_fused_est_only_and_identity_mask(sep, oracle):
     """mask == 1 for a single source: est must reproduce the mixture (perfect reconstruction)."""
     rng = np.random.default_rng(1)
