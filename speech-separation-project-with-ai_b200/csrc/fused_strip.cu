@@ -403,7 +403,8 @@ static int launch_strip_w(const sep_plan *p, FusedArgs a, int batch, double *d_s
                           Scratch &s, cudaStream_t stream) {
   using G = StripGeom<C, R, SCORE, W>;
   const int sms = p->sm_count > 0 ? p->sm_count : 148;
-  pick_strips(a.T, G::H, 4, batch, sms * W * CTAS_PER_SM, &a.tiles, &a.strip_iters);
+  static const int plan_env = getenv("SEPCORE_STRIP_WARPS") ? atoi(getenv("SEPCORE_STRIP_WARPS")) : 0;
+  pick_strips(a.T, G::H, 4, batch, plan_env > 0 ? plan_env : sms * W * CTAS_PER_SM, &a.tiles, &a.strip_iters);
   int rc;
   double *partials = nullptr;
   int *counters = nullptr;

@@ -418,7 +418,12 @@ static int launch_strip512(const sep_plan *p, FusedArgs a, int batch, double *d_
   constexpr int W = 4, CTAS_PER_SM = 8 / W;
   using G = Strip512Geom<C, SCORE, W>;
   const int sms = p->sm_count > 0 ? p->sm_count : 148;
-  pick_strips(a.T, G::H, G::FPI, batch, sms * 8, &a.tiles, &a.strip_iters);
+  static const int plan_env = getenv("SEPCORE_STRIP_WARPS") ? atoi(getenv("SEPCORE_STRIP_WARPS")) : 0;
+  // planned for half of the resident warps at small batches: fewer, longer strips (three halo frames each) --
+  // in a stream of independent steps the other launches fill the SMs (cfg4: 172 -> 164 us per step; a launch
+  // alone 197 -> 263 us); see fused_wstrip.cu
+  pick_strips(a.T, G::H, G::FPI, batch, plan_env > 0 ? plan_env : (batch >= 2 * sms ? sms * 8 : sms * 4), &a.tiles,
+              &a.strip_iters);
   int rc;
   double *partials = nullptr;
   int *counters = nullptr;
