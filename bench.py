@@ -418,8 +418,9 @@ def run_sepcore(args):
                          "peak": peak, "unit": "GB/s",
                          "frac": bytes_per_launch / (ms_total / args.steps * 1e-3) / 1e9 / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "strip256_kernel (256/{128,64}, C<=2) / strip512_kernel (512/128) / tile or generic "
-                                   "kernel otherwise; CUDA events around the timed region on the launching stream",
+                         "kernel": "wstrip256_kernel (256/{128,64}, C=2) / strip256_kernel (C=1) / strip512_kernel (512/128) / "
+                                   "tile or generic kernel otherwise; CUDA events around the timed region on the "
+                                   "launching stream",
                          "kernel_ms": ms_total / args.steps, "bytes_per_launch": bytes_per_launch,
                          "launches_timed": args.steps,
                          "alone": {"kernel_ms": kernel_ms_avg, "achieved": achieved, "frac": achieved / peak,

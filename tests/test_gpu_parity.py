@@ -514,9 +514,9 @@ def test_host_pipeline_and_graph_match_sync_call(sep, oracle):
 
 
 def test_single_launch_finalisation_matches(sep, oracle, monkeypatch):
-    """SEPCORE_SINGLE_LAUNCH=1 folds the finalisation into the fused kernel (last tile of an
-    utterance finalises it): same arithmetic, bit-identical scores.  Run in a subprocess
-    because the switch is read once per process."""
+    """By default the finalisation is folded into the fused kernel (the last strip of an utterance
+    finalises it); SEPCORE_SINGLE_LAUNCH=0 runs it as separate kernels: same arithmetic, bit-identical
+    scores.  Run in subprocesses because the switch is read once per process."""
     import subprocess, sys, os, textwrap
     code = textwrap.dedent("""
         import sys, numpy as np
@@ -533,12 +533,10 @@ def test_single_launch_finalisation_matches(sep, oracle, monkeypatch):
             os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                          "speech-separation-project-with-ai_b200"))
     outs = []
-    for flag in ("", "1"):
+    for flag in ("0", "1"):
         env = dict(os.environ)
-        env.pop("SEPCORE_SINGLE_LAUNCH", None)
-        if flag:
-            env["SEPCORE_SINGLE_LAUNCH"] = flag
-        path = "/tmp/sepcore_single_%s.npy" % (flag or "0")
+        env["SEPCORE_SINGLE_LAUNCH"] = flag
+        path = "/tmp/sepcore_single_%s.npy" % flag
         subprocess.run([sys.executable, "-c", code, path], check=True, env=env)
         outs.append(np.load(path))
     assert np.array_equal(outs[0], outs[1])
