@@ -1,13 +1,5 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/w12_tests.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/w12_smoke.log 2>&1
-B="python bench.py --steps 400 --warmup 10 --no-cpu-baseline --no-e2e"
-$B > gpurun_out/w12_cfg2.log 2>&1
-SEPCORE_SINGLE_LAUNCH=0 $B > gpurun_out/w12_cfg2_multi.log 2>&1
-$B --shift 64 --window hann > gpurun_out/w12_hop64.log 2>&1
-SEPCORE_SINGLE_LAUNCH=0 $B --shift 64 --window hann > gpurun_out/w12_hop64_multi.log 2>&1
-$B --sources 1 > gpurun_out/w12_c1.log 2>&1
-SEPCORE_SINGLE_LAUNCH=0 $B --sources 1 > gpurun_out/w12_c1_multi.log 2>&1
-$B --steps 100 --size 512 --shift 128 --sources 3 --seconds 8 --window hann > gpurun_out/w12_cfg4.log 2>&1
-SEPCORE_SINGLE_LAUNCH=0 $B --steps 100 --size 512 --shift 128 --sources 3 --seconds 8 --window hann > gpurun_out/w12_cfg4_multi.log 2>&1
-$B --streams 8 > gpurun_out/w12_cfg2_s8.log 2>&1
-$B --streams 4 > gpurun_out/w12_cfg2_s4.log 2>&1
+python bench.py --steps 1000 --warmup 10 > gpurun_out/w13_bench_full.log 2>&1
+python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/w13_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1_final.csv python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/w13_ncu_launches.log 2>&1
+python tools/run_steps.py --steps 6 > gpurun_out/w13_plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:wstrip256 -s 3 -c 1 -f -o gpurun_out/prof_wstrip_v5 python tools/run_steps.py --steps 6 > gpurun_out/w13_ncu.log 2>&1
+python tools/bench_scoring.py > gpurun_out/w13_scoring.log 2>&1
+python tools/bench_filterbank.py > gpurun_out/w13_fb.log 2>&1
