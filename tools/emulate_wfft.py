@@ -13,7 +13,7 @@ def wfft256(V, inv=False):
     for q in range(32):
         V[q] = np.array([sum(V[q, m] * W(8, m * k0, inv) for m in range(8)) for k0 in range(8)])
         V[q] *= np.array([W(256, q * k0, inv) for k0 in range(8)])
-    # exchange 1: A[k0][q], pitch 34; lane (k0, h) = k0 + 8 h reads pairs at A[k0][2h + 8 q1]
+    # exchange 1 (its own region): A[k0][q], pitch 34; lane (k0, h) = k0 + 8 h reads pairs at A[k0][2h + 8 q1]
     A = np.zeros(8 * 34, complex)
     for q in range(32):
         for k0 in range(8):
@@ -32,16 +32,19 @@ def wfft256(V, inv=False):
             for k1 in range(4):
                 out[2 * k1 + e] = sum(U[lam, 2 * q1 + e] * W(4, q1 * k1, inv) for q1 in range(4)) * W(32, (2 * h + e) * k1, inv)
         U[lam] = out
-    # exchange 2: B[row = k0 + 8 k1][q0], pitch 10
+    # exchange 2: row k0 + 8 k1 (pitch 10), column h + 4 e holds q0 = 2 h + e (64-bit stores without bank conflicts)
     B = np.zeros(32 * 10, complex)
     for lam in range(32):
         k0, h = lam & 7, lam >> 3
         for k1 in range(4):
-            B[(k0 + 8 * k1) * 10 + 2 * h] = U[lam, 2 * k1]
-            B[(k0 + 8 * k1) * 10 + 2 * h + 1] = U[lam, 2 * k1 + 1]
+            B[(k0 + 8 * k1) * 10 + h] = U[lam, 2 * k1]
+            B[(k0 + 8 * k1) * 10 + h + 4] = U[lam, 2 * k1 + 1]
     out = np.zeros((32, 8), complex)
     for l in range(32):
-        v = B[l * 10:l * 10 + 8]
+        row = B[l * 10:l * 10 + 8]
+        v = np.zeros(8, complex)
+        # the four 128-bit reads: columns (0,1) (2,3) (4,5) (6,7) = q0 (0,2) (4,6) (1,3) (5,7)
+        v[0], v[2], v[4], v[6], v[1], v[3], v[5], v[7] = row
         out[l] = np.array([sum(v[q0] * W(8, q0 * k2, inv) for q0 in range(8)) for k2 in range(8)])
     return out
 
