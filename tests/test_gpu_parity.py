@@ -403,6 +403,31 @@ def test_fused_two_strip_kernels_agree(sep, oracle, monkeypatch, key, n, batch):
         assert np.allclose(res["pit_pair"][0], want["pit"]["pair"][0], rtol=1e-4)
 
 
+def test_fused_many_short_utterances(sep, oracle, monkeypatch):
+    """More strips than resident warps (2000 utterances of 0.25 s: every warp of the persistent grid walks
+    several strips, batch >= 2 x SMs takes the two-wave strip plan): a few utterances against the oracle,
+    all of them against the half-warp kernel."""
+    cfg = CONFIGS["blackman_256_128"]
+    rng = np.random.default_rng(77)
+    batch, n = 2000, 2000
+    mix, refs, masks, lengths = _fused_case(rng, batch, n, 2, cfg, oracle, ragged=True)
+    res = sep.separate_and_score(mix, masks, refs, frame_lengths=lengths, **cfg)
+    for b in (0, 1, 777, 1999):
+        want = oracle.separate_and_score(mix[b], refs[b], masks[b], length=lengths[b], **cfg)
+        assert rel_err(res["est"][b], want["ests"][:, :n]) < TOL_REL
+        assert int(res["pit_perm"][b]) == int(want["pit"]["idx"][0])
+        assert np.allclose(res["pit_pair"][b], want["pit"]["pair"][0], rtol=1e-4)
+        assert np.max(np.abs(res["si_pair"][b] - want["si_sdr_pair"])) < TOL_DB
+    monkeypatch.setenv("SEPCORE_FORCE_HALFWARP", "1")
+    old = sep.separate_and_score(mix, masks, refs, frame_lengths=lengths, **cfg)
+    monkeypatch.delenv("SEPCORE_FORCE_HALFWARP")
+    assert rel_l2(res["est"], old["est"]) < 2e-6
+    assert np.array_equal(res["pit_perm"], old["pit_perm"])
+    assert np.allclose(res["pit_loss"], old["pit_loss"], rtol=1e-5)
+    assert abs(res["sums"][0] - old["sums"][0]) < 1e-6 * abs(old["sums"][0])
+    assert res["sums"][3] == batch
+
+
 def test_fused_est_only_and_identity_mask(sep, oracle):
     """mask == 1 for a single source: est must reproduce the mixture (perfect reconstruction)."""
     rng = np.random.default_rng(1)
@@ -413,12 +438,14 @@ def test_fused_est_only_and_identity_mask(sep, oracle):
     assert oracle.si_sdr(mix[0].astype(np.float64), res["est"][0, 0].astype(np.float64)) > 100.0
 
 
-def test_fused_device_tensors_full_size(sep, oracle):
-    """BASELINE config 2 at full size (64 x 4 s, C=2), device-resident tensors;
-    checked through size-independent properties + a few utterances vs the oracle."""
+@pytest.mark.parametrize("key", ["blackman_256_128", "hann_256_64"])
+def test_fused_device_tensors_full_size(sep, oracle, key):
+    """BASELINE config 2 at full size (64 x 4 s, C=2; the reference's Blackman 256/128 and BASELINE's Hann
+    256/64), device-resident tensors; checked through size-independent properties + a few utterances vs
+    the oracle."""
     import torch
     rng = np.random.default_rng(2)
-    cfg = CONFIGS["blackman_256_128"]
+    cfg = CONFIGS[key]
     mix, refs, masks, _ = _fused_case(rng, 64, 32000, 2, cfg, oracle)
     dm, dr, dk = (torch.from_numpy(a).cuda() for a in (mix, refs, masks))
     res = sep.separate_and_score(dm, dk, dr, **cfg)
