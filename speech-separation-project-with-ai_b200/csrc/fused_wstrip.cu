@@ -400,6 +400,54 @@ __global__ void __launch_bounds__(W * 32, CPS) wstrip256_kernel(const FusedArgs 
           }
         }
       };
+      // both estimates at once (two sources): the reference samples are read and converted once for the four
+      // Gram products instead of once per estimate
+      auto finish2 = [&](const float2 (&va)[8], const float2 (&vb)[8]) {
+        float y0[NY], y1[NY];
+        {
+          const float4 w0 = synp[0], w1 = synp[1];
+          const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int mm = 0; mm < NY; ++mm) {
+            float t0 = mm < NCARRY ? carry[0][mm] : 0.f, t1 = mm < NCARRY ? carry[C - 1][mm] : 0.f;
+            if (mm >= D) { t0 = fmaf(va[mm - D].y, w[mm - D], t0); t1 = fmaf(vb[mm - D].y, w[mm - D], t1); }
+            if (mm < 8) { t0 = fmaf(va[mm].x, w[mm], t0); t1 = fmaf(vb[mm].x, w[mm], t1); }
+            y0[mm] = t0;
+            y1[mm] = t1;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < NCARRY; ++k) { carry[0][k] = y0[NOUT + k]; carry[C - 1][k] = y1[NOUT + k]; }
+        float *out0 = a.est ? a.est + static_cast<int64_t>(b) * C * a.n + gb : nullptr;
+        float *out1 = a.est ? out0 + a.n : nullptr;
+        // one straight-line copy per case: whole hop blocks inside the utterance / blocks on an edge
+        auto emit = [&](auto plain_tag) {
+          constexpr bool PLAIN = decltype(plain_tag)::value;
+          if (out0) {
+#pragma unroll
+            for (int mm = 0; mm < NOUT; ++mm) {
+              if (PLAIN || (mm >= skip && mm < lim)) { out0[32 * mm] = y0[mm]; out1[32 * mm] = y1[mm]; }
+            }
+          }
+          if (SCORE) {
+            double g00 = 0.0, g01 = 0.0, g10 = 0.0, g11 = 0.0, e0 = 0.0, e1 = 0.0, r0 = 0.0, r1 = 0.0;
+#pragma unroll
+            for (int mm = 0; mm < NOUT; ++mm) {
+              const bool okv = PLAIN || (mm >= skip && mm < lim_v);
+              const double a0 = okv ? static_cast<double>(y0[mm]) : 0.0, a1 = okv ? static_cast<double>(y1[mm]) : 0.0;
+              const double b0 = okv ? static_cast<double>(st[SPAN + 32 * mm]) : 0.0;
+              const double b1 = okv ? static_cast<double>(st[2 * SPAN + 32 * mm]) : 0.0;
+              e0 = fma(a0, a0, e0); e1 = fma(a1, a1, e1);
+              g00 = fma(a0, b0, g00); g01 = fma(a0, b1, g01);
+              g10 = fma(a1, b0, g10); g11 = fma(a1, b1, g11);
+              r0 = fma(b0, b0, r0); r1 = fma(b1, b1, r1);
+            }
+            acc[32 * 0] += g00; acc[32 * 1] += g01; acc[32 * 2] += g10; acc[32 * 3] += g11;
+            acc[32 * 4] += e0; acc[32 * 5] += e1; acc[32 * 6] += r0; acc[32 * 7] += r1;
+          }
+        };
+        if (plain) emit(std::true_type{}); else emit(std::false_type{});
+      };
       using Q0 = std::integral_constant<int, 0>;
       using Q1 = std::integral_constant<int, C - 1>;
       if constexpr (C == 2 && DUAL) {
@@ -408,8 +456,7 @@ __global__ void __launch_bounds__(W * 32, CPS) wstrip256_kernel(const FusedArgs 
         masked(vb, Q1{});
         if (it + 1 < n_it) load_masks(ta + 2);                      // next iteration's masks, a transform ahead
         wfft256x2<true>(v, vb, t1, t2, ex, lane);
-        finish(v, Q0{});
-        finish(vb, Q1{});
+        finish2(v, vb);
       } else {
         masked(v, Q0{});
         if (C == 1 && it + 1 < n_it) load_masks(ta + 2);
