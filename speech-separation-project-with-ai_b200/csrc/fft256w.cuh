@@ -59,39 +59,52 @@ __device__ __forceinline__ void fft8(float2 (&v)[8]) {
 // ex: an exchange buffer of kWxFloat2 float2 (X1 rows, then X2 rows).  Two exchange regions: the reads of
 // one are ordered before the next writes of the same region by the barrier of the OTHER exchange, so a
 // transform needs two warp barriers, not four.
-template <bool INV>
-__device__ __forceinline__ void wfft_phase1(float2 (&v)[8], const float2 *t1, float2 *ex, int q) {
-  fft8<INV>(v);
+// twiddle rows of a lane: tw1[1..7] = W256^(q k0), tw2[2..7] = W32^(q0 k1) (entries 0 / 0, 1 are ones)
+struct WTwiddles {
+  float2 a[8], b[8];
+};
+__device__ __forceinline__ void wfft_load_tw1(WTwiddles &t, const float2 *t1) {
   const float4 *t14 = reinterpret_cast<const float4 *>(t1);
 #pragma unroll
   for (int k = 0; k < 8; k += 2) {
     const float4 w = t14[k / 2];
-    if (k > 0) v[k] = cmul(v[k], make_float2(w.x, INV ? -w.y : w.y));
-    v[k + 1] = cmul(v[k + 1], make_float2(w.z, INV ? -w.w : w.w));
+    t.a[k] = make_float2(w.x, w.y);
+    t.a[k + 1] = make_float2(w.z, w.w);
   }
+}
+__device__ __forceinline__ void wfft_load_tw2(WTwiddles &t, const float2 *t2) {
+  const float4 *t24 = reinterpret_cast<const float4 *>(t2);
+#pragma unroll
+  for (int i = 2; i < 8; i += 2) {
+    const float4 w = t24[i / 2];
+    t.b[i] = make_float2(w.x, w.y);
+    t.b[i + 1] = make_float2(w.z, w.w);
+  }
+}
+
+template <bool INV>
+__device__ __forceinline__ void wfft_phase1(float2 (&v)[8], const WTwiddles &t, float2 *ex, int q) {
+  fft8<INV>(v);
+#pragma unroll
+  for (int k = 1; k < 8; ++k) v[k] = cmul(v[k], make_float2(t.a[k].x, INV ? -t.a[k].y : t.a[k].y));
 #pragma unroll
   for (int k = 0; k < 8; ++k) ex[k * kWxA + q] = v[k];
 }
 
 template <bool INV>
-__device__ __forceinline__ void wfft_phase2(float2 (&v)[8], const float2 *t2, float2 *ex, int q) {
+__device__ __forceinline__ void wfft_phase2(float2 (&v)[8], const WTwiddles &t, float2 *ex, int q) {
   const int k0 = q & 7, h = q >> 3;
   const float4 *ra = reinterpret_cast<const float4 *>(ex + k0 * kWxA + 2 * h);
 #pragma unroll
   for (int q1 = 0; q1 < 4; ++q1) {
-    const float4 t = ra[4 * q1];
-    v[2 * q1] = make_float2(t.x, t.y);
-    v[2 * q1 + 1] = make_float2(t.z, t.w);
+    const float4 r = ra[4 * q1];
+    v[2 * q1] = make_float2(r.x, r.y);
+    v[2 * q1 + 1] = make_float2(r.z, r.w);
   }
   fft4<INV>(v[0], v[2], v[4], v[6]);
   fft4<INV>(v[1], v[3], v[5], v[7]);
-  const float4 *t24 = reinterpret_cast<const float4 *>(t2);
 #pragma unroll
-  for (int i = 2; i < 8; i += 2) {
-    const float4 w = t24[i / 2];
-    v[i] = cmul(v[i], make_float2(w.x, INV ? -w.y : w.y));
-    v[i + 1] = cmul(v[i + 1], make_float2(w.z, INV ? -w.w : w.w));
-  }
+  for (int i = 2; i < 8; ++i) v[i] = cmul(v[i], make_float2(t.b[i].x, INV ? -t.b[i].y : t.b[i].y));
   // X2: row k0 + 8 k1, column h + 4 e holds q0 = 2 h + e (64-bit stores: no register quads to assemble; the 16
   // lanes of a half-warp -- k0 = 0..7, two values of h -- hit 16 distinct 8-byte banks)
   float2 *wb = ex + kWxOne + k0 * kWxB + h;
@@ -116,24 +129,30 @@ __device__ __forceinline__ void wfft_phase3(float2 (&v)[8], const float2 *ex, in
 // v[j] = x[q + 32 j] -> v[j] = X[q + 32 j].
 template <bool INV>
 __device__ __forceinline__ void wfft256(float2 (&v)[8], const float2 *t1, const float2 *t2, float2 *ex, int q) {
-  wfft_phase1<INV>(v, t1, ex, q);
+  WTwiddles t;
+  wfft_load_tw1(t, t1);
+  wfft_phase1<INV>(v, t, ex, q);
+  wfft_load_tw2(t, t2);
   __syncwarp();
-  wfft_phase2<INV>(v, t2, ex, q);
+  wfft_phase2<INV>(v, t, ex, q);
   __syncwarp();
   wfft_phase3<INV>(v, ex, q);
 }
 
 // Two independent transforms in lockstep (exchange buffers ex and ex + kWxFloat2): twice the independent
 // instructions between the same two barriers, so the shared-memory round trips of one hide behind the
-// butterflies of the other.
+// butterflies of the other; the twiddle rows are read once for both.
 template <bool INV>
 __device__ __forceinline__ void wfft256x2(float2 (&va)[8], float2 (&vb)[8], const float2 *t1, const float2 *t2,
                                           float2 *ex, int q) {
-  wfft_phase1<INV>(va, t1, ex, q);
-  wfft_phase1<INV>(vb, t1, ex + kWxFloat2, q);
+  WTwiddles t;
+  wfft_load_tw1(t, t1);
+  wfft_phase1<INV>(va, t, ex, q);
+  wfft_phase1<INV>(vb, t, ex + kWxFloat2, q);
+  wfft_load_tw2(t, t2);
   __syncwarp();
-  wfft_phase2<INV>(va, t2, ex, q);
-  wfft_phase2<INV>(vb, t2, ex + kWxFloat2, q);
+  wfft_phase2<INV>(va, t, ex, q);
+  wfft_phase2<INV>(vb, t, ex + kWxFloat2, q);
   __syncwarp();
   wfft_phase3<INV>(va, ex, q);
   wfft_phase3<INV>(vb, ex + kWxFloat2, q);
