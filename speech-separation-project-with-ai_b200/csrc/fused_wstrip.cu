@@ -22,8 +22,9 @@
 // free), the PIT / Gram arithmetic, the partial rows and the finalisation are those of fused_strip.cu,
 // so results agree with the half-warp kernel to float32 round-off
 // (tests/test_gpu_parity.py::test_fused_two_strip_kernels_agree).
-// Measured (profiles/r1_ncu_wstrip.md): 23.9 us per cfg2 step in the replayed loop against 24.8 us for the
-// half-warp strips, 188 against 206 us at batch 512; with one source the half-warp strips stay faster.
+// Measured (profiles/r1_ncu_wstrip.md): 21.9 us per cfg2 step in the replayed loop against 24.8 us for the
+// half-warp strips (separate finalisation kernels), 180 against 206 us at batch 512; with one source the half-warp
+// strips stay faster.
 // Reference lines: see fused.cu.
 #include <algorithm>
 #include <cstdlib>
