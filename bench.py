@@ -252,10 +252,14 @@ def run_sepcore(args):
     warm.replay()
     if world > 1:
         dist.all_reduce(warm.sums)           # warms NCCL up too
-    barrier()
     sampler = ClockSampler(local)
     sampler.start()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    if world > 1:
+        # device-side rendezvous right in front of the start event: the ranks leave the host barrier at slightly
+        # different times, and the all-reduce inside the timed region would charge that skew to every rank
+        dist.all_reduce(torch.zeros(1, device=dev))
     start.record()
     for _ in range(n_blocks):
         graph.replay()
