@@ -163,11 +163,14 @@ __device__ __forceinline__ void wfft256x2(float2 (&va)[8], float2 (&vb)[8], cons
 // meaningful on lane 0 only).
 __device__ __forceinline__ void wsplit_planar(const float2 (&v)[8], int q, int r, float2 &XR, float2 &XI) {
   const int src = (32 - q) & 31;
-  float2 got;
-  got.x = __shfl_sync(0xffffffffu, v[r < 4 ? 7 - r : 3].x, src);
-  got.y = __shfl_sync(0xffffffffu, v[r < 4 ? 7 - r : 3].y, src);
-  const float2 own = v[(8 - r) & 7];
-  const float2 zp = (q == 0) ? own : got;
+  float2 zp = v[4];                      // r == 4: bin 128 is its own partner (and lives on lane 0 only)
+  if (r < 4) {
+    float2 got;
+    got.x = __shfl_sync(0xffffffffu, v[7 - r].x, src);
+    got.y = __shfl_sync(0xffffffffu, v[7 - r].y, src);
+    const float2 own = v[(8 - r) & 7];
+    zp = (q == 0) ? own : got;
+  }
   const float2 z = v[r];
   XR = __fadd2_rn(z, zp);                                                  // (zx + z'x, zy + z'y)
   XI = __fadd2_rn(make_float2(z.y, -z.x), make_float2(-zp.y, zp.x));       // (zy - z'y, z'x - zx)
