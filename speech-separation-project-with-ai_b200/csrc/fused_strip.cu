@@ -404,7 +404,11 @@ static int launch_strip_w(const sep_plan *p, FusedArgs a, int batch, double *d_s
   using G = StripGeom<C, R, SCORE, W>;
   const int sms = p->sm_count > 0 ? p->sm_count : 148;
   static const int plan_env = getenv("SEPCORE_STRIP_WARPS") ? atoi(getenv("SEPCORE_STRIP_WARPS")) : 0;
-  pick_strips(a.T, G::H, 4, batch, plan_env > 0 ? plan_env : sms * W * CTAS_PER_SM, &a.tiles, &a.strip_iters);
+  // planned for one wave of W-warp CTAs at small batches: fewer, longer strips; in a stream of independent steps the
+  // other launches fill the SMs (one source, 64 x 4 s: 14.3 -> 13.2 us per step; a launch alone 29 -> 34 us); see
+  // fused_wstrip.cu
+  pick_strips(a.T, G::H, 4, batch, plan_env > 0 ? plan_env : (batch >= 2 * sms ? sms * W * CTAS_PER_SM : sms * W),
+              &a.tiles, &a.strip_iters);
   int rc;
   double *partials = nullptr;
   int *counters = nullptr;
