@@ -131,3 +131,31 @@ def test_score_layout_matches_library():
     from sepcore import _lib
     for c in (1, 2, 3, 4):
         assert sepcore.score_layout(c)["stride"] == _lib.load().sep_score_stride(c)
+
+
+def test_warp_fft_index_algebra_emulation():
+    """tools/emulate_wfft.py restates the lane / register / shared-memory index algebra of csrc/fft256w.cuh
+    (8 x 4 x 8 whole-warp FFT, both exchanges, pair split and Hermitian merge) in numpy: it must reproduce
+    numpy.fft -- the layout rules the kernel is written against."""
+    import importlib.util
+    import numpy as np
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("emulate_wfft", os.path.join(root, "tools", "emulate_wfft.py"))
+    em = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(em)
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(256) + 1j * rng.standard_normal(256)
+    X = em.from_lanes(em.wfft256(em.to_lanes(x)))
+    assert np.abs(X - np.fft.fft(x)).max() < 1e-10
+    assert np.abs(em.from_lanes(em.wfft256(em.to_lanes(X), inv=True)) / 256 - x).max() < 1e-12
+    a, b = rng.standard_normal(256), rng.standard_normal(256)
+    XA, XB = em.split_planar(em.wfft256(em.to_lanes(0.5 * (a + 1j * b))))
+    FA, FB = np.fft.rfft(a), np.fft.rfft(b)
+    for q in range(32):
+        for r in range(5):
+            k = q + 32 * r
+            if k <= 128 and (r < 4 or q == 0):
+                assert abs(XA[q, r] - FA[k]) < 1e-10 and abs(XB[q, r] - FB[k]) < 1e-10
+    y = em.from_lanes(em.wfft256(em.merge_pair(XA + 1j * XB, np.conj(XA) + 1j * np.conj(XB)), inv=True)) / 256
+    assert np.abs(y.real - a).max() < 1e-12 and np.abs(y.imag - b).max() < 1e-12
