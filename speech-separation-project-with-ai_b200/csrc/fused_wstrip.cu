@@ -58,6 +58,8 @@ struct WStripGeom {
   static constexpr int NV = FusedVals<C>::NV;
 };
 
+// Built and tested for C = 2, DUAL = true (dispatch_wstrip); the C = 1 / one-transform-at-a-time branches are what the
+// measurements in profiles/r1_ncu_wstrip.md compared against and are not instantiated in the library.
 template <int C, int R, bool SCORE, int W, int CPS, bool DUAL>
 __global__ void __launch_bounds__(W * 32, CPS) wstrip256_kernel(const FusedArgs a) {
   using G = WStripGeom<C, R, SCORE, W, DUAL>;
