@@ -237,6 +237,11 @@ int sep_pcm16_to_f32(const int16_t *pcm, int64_t n, float *out, int mem, void *s
  * clipped may be NULL.  Arithmetic is float32 like numpy's on a float32 array. */
 int sep_audiowrite_i16_f32(const float *data, int batch, int64_t n, int normalize, int16_t *out,
                            int64_t *clipped, int mem, void *stream);
+/* The same conversion in float64 -- the dtype the reference's istft (cell 39) hands to audiowrite (cell 41
+ * :1403-1404): numpy keeps a float64 array in float64, so truncation happens on the float64 product.
+ * An all-zero row with normalize=1 is 0/0 = NaN in the reference, which astype(np.int16) turns into 0. */
+int sep_audiowrite_i16_f64(const double *data, int batch, int64_t n, int normalize, int16_t *out,
+                           int64_t *clipped, int mem, void *stream);
 
 #ifdef __cplusplus
 }

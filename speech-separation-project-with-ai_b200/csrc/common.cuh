@@ -301,4 +301,12 @@ __device__ __forceinline__ void nth_permutation(int n, int p, int *out) {
 
 #endif  // __CUDACC__
 
+// In-kernel finalisation counters ([batch + 1] ints) are zeroed before every launch -- also when they live in
+// a caller workspace that the previous launch left at zero: a launch that was aborted half way must not poison
+// every later call on that workspace.  The reset is a 4 (batch + 1)-byte memset node on the launch stream.
+inline int reset_counters(int *counters, int batch, const Scratch &, cudaStream_t stream) {
+  SEP_CUDA(cudaMemsetAsync(counters, 0, sizeof(int) * (static_cast<size_t>(batch) + 1), stream));
+  return SEP_OK;
+}
+
 }  // namespace sep

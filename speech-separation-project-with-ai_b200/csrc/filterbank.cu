@@ -435,8 +435,9 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
           tc_fence_before();
           mbar_arrive(SEP_BAR(kBarD1Free));
         }
-        // frames beyond the utterance are all-zero rows of A1: their code is relu(0) = 0, so the
-        // (finite) mask values of whatever rows the tile covers there never matter
+        // frames beyond the utterance are all-zero rows of A1 (code = relu(0) = 0), but the mask rows the TMA tile
+        // covers there belong to the NEXT (b, c) plane (or are the tile's zero fill): a non-finite mask value
+        // would turn 0 * inf into NaN, so those rows' products are forced to zero below
 #pragma unroll
         for (int e = 0; e < kFbChunk; ++e) d[e] = fmaxf(d[e], 0.f);
         const uint32_t slot = fills % kFbStages;
@@ -448,6 +449,10 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
           const float4 mk = *reinterpret_cast<const float4 *>(mk_s + ((q ^ sw) << 4));
           p[2 * q] = __fmul2_rn(make_float2(d[4 * q], d[4 * q + 1]), make_float2(mk.x, mk.y));
           p[2 * q + 1] = __fmul2_rn(make_float2(d[4 * q + 2], d[4 * q + 3]), make_float2(mk.z, mk.w));
+        }
+        if (!row_ok) {
+#pragma unroll
+          for (int q = 0; q < kFbChunk / 2; ++q) p[q] = make_float2(0.f, 0.f);
         }
         ++fills;
         float hi[kFbChunk], lo[kFbChunk];
@@ -605,6 +610,11 @@ extern "C" int sep_filterbank_separate_f32(const float *wave, const float *enc, 
   if ((rc = stage_in(s, masks, n_mask, mem, &a.masks))) return rc;
   if ((rc = stage_out(s, est, n_est, mem, &a.est))) return rc;
   if ((rc = stage_out(s, code, n_code, mem, &a.code))) return rc;
+  // float4 loads of the frames and float4 stores of the estimates: a contiguous but offset device view
+  // (buf[1:]) would fault with a misaligned address inside the kernel, so refuse it here
+  SEP_REQUIRE((reinterpret_cast<uintptr_t>(a.wave) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.est) & 15) == 0 &&
+                  (a.code == nullptr || (reinterpret_cast<uintptr_t>(a.code) & 15) == 0),
+              "sep_filterbank_separate_f32: wave, est and code must be 16-byte aligned");
   a.n = n_samples;
   a.est_len = est_len;
   a.n_src = n_src;

@@ -19,7 +19,6 @@ struct FusedArgs {
   int *counters;          // [B + 1] zero on entry, left zero: tiles done per utterance, utterances done
   int64_t n;
   int T, size, shift, pad, tb, tiles;
-  int debug_skip;   // developer timing aid (SEPCORE_DEBUG_SKIP): bit0 refs+PIT, bit1 inverse+OLA, bit2 gather, bit3 mix FFT
   int batch, lookahead;   // lookahead: tiles ahead of this CTA to pull into L2 (0 = off)
   int strip_iters, vec_ok;  // strip kernel: iterations per utterance; rows 16-byte aligned
   const float *win_half, *syn;

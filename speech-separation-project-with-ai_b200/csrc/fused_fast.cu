@@ -69,7 +69,6 @@ __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedAr
 
   // ---- stage waveforms asynchronously (zeros outside [0, n)), clear accumulators ----
   constexpr int NSIG = SCORE ? 1 + C : 1;
-  if (!(a.debug_skip & 32))
 #pragma unroll
   for (int sgn = 0; sgn < NSIG; ++sgn) {
     const float *row = sgn == 0 ? a.mix + static_cast<int64_t>(b) * a.n
@@ -87,7 +86,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedAr
     }
   }
   // pull the tile that a CTA of the next wave will stage into L2 (no registers, no smem)
-  if (a.lookahead > 0 && threadIdx.x == 0 && !(a.debug_skip & 64)) {
+  if (a.lookahead > 0 && threadIdx.x == 0) {
     const int64_t next = static_cast<int64_t>(b) * a.tiles + tile + a.lookahead;
     const int nb = static_cast<int>(next / a.tiles), nt = static_cast<int>(next - static_cast<int64_t>(nb) * a.tiles);
     if (nb < a.batch) {
@@ -130,8 +129,8 @@ __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedAr
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
       const bool bin_ok = r < 8 || l16 == 0;
-      ma[q][r] = (bin_ok && ta < T && !(a.debug_skip & 16)) ? __ldg(base + static_cast<int64_t>(ta) * 129 + l16 + 16 * r) : 0.f;
-      mb[q][r] = (bin_ok && tb < T && !(a.debug_skip & 16)) ? __ldg(base + static_cast<int64_t>(tb) * 129 + l16 + 16 * r) : 0.f;
+      ma[q][r] = (bin_ok && ta < T) ? __ldg(base + static_cast<int64_t>(ta) * 129 + l16 + 16 * r) : 0.f;
+      mb[q][r] = (bin_ok && tb < T) ? __ldg(base + static_cast<int64_t>(tb) * 129 + l16 + 16 * r) : 0.f;
     }
   }
   const float2 *tw = twt + l16;
@@ -152,14 +151,14 @@ __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedAr
     v[m] = cscale(make_float2(tiles[SEP_POS_A(m)], tiles[SEP_POS_B(m)]), w.x);
     v[m + 1] = cscale(make_float2(tiles[SEP_POS_A(m + 1)], tiles[SEP_POS_B(m + 1)]), w.y);
   }
-  if (!(a.debug_skip & 8)) fft256<false>(v, tw, xch, l16);
+  fft256<false>(v, tw, xch, l16);
   float2 Xa[9], Xb[9];
   split_pair(v, l16, Xa, Xb);
 
   float pit[C * C];
 #pragma unroll
   for (int i = 0; i < C * C; ++i) pit[i] = 0.f;
-  if (SCORE && !(a.debug_skip & 1)) {
+  if (SCORE) {
     const float len_f = a.lengths ? a.lengths[b] : static_cast<float>(T);
     const int len_i = static_cast<int>(len_f);
     // weights: frame counted once (owned), prediction gated by t < length (cell 28 :1031-1046)
@@ -206,7 +205,6 @@ __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedAr
   }
 
   // ---- masked spectra -> time frames -> phased overlap-add ----
-  if (!(a.debug_skip & 2))
 #pragma unroll
   for (int q = 0; q < C; ++q) {
     float2 L[9], Mi[9];
@@ -250,7 +248,6 @@ __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedAr
   const int span = (j1 - j0) * SHIFT;
   const int first = (j0 - t_lo) * SHIFT;                      // accumulator index of output sample 0
   const int64_t g0 = static_cast<int64_t>(j0) * SHIFT - a.pad;   // its original sample index
-  if (!(a.debug_skip & 4))
   for (int i = threadIdx.x; i < span; i += kFastThreads) {
     const int64_t g = g0 + i;
     if (g >= a.n) break;
@@ -277,7 +274,7 @@ __global__ void __launch_bounds__(kFastThreads, 3) fused256_kernel(const FusedAr
   }
 #undef SEP_POS_A
 #undef SEP_POS_B
-  if (!SCORE || (a.debug_skip & 128)) return;
+  if (!SCORE) return;
   constexpr int NV = G::NV;
   double vals[NV];
 #pragma unroll
@@ -314,14 +311,14 @@ static int launch_fast(FusedArgs a, int batch, double *d_scores, double *d_sums,
     if ((rc = s.alloc(&counters, static_cast<size_t>(batch) + 1))) return rc;
     if ((rc = s.alloc(&partials, static_cast<size_t>(batch) * a.tiles * G::NV))) return rc;
     if (!single_launch) counters = nullptr;
-    else if (!s.arena) SEP_CUDA(cudaMemsetAsync(counters, 0, sizeof(int) * (batch + 1), stream));
+    else if ((rc = reset_counters(counters, batch, s, stream))) return rc;
   }
   a.partials = partials;
   a.counters = counters;
   a.scores = d_scores;
   a.sums = d_sums;
   a.lookahead = 148 * 3;
-  { const char *dbg = getenv("SEPCORE_DEBUG_SKIP"); a.debug_skip = dbg ? atoi(dbg) : 0; }   // one wave of resident CTAs (3 per SM)
+  // one wave of resident CTAs (3 per SM)
   const size_t smem = G::smem(SCORE);
   SEP_CUDA(cudaFuncSetAttribute(fused256_kernel<C, R, SCORE>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

@@ -434,7 +434,7 @@ static int launch_strip512(const sep_plan *p, FusedArgs a, int batch, double *d_
     if ((rc = s.alloc(&counters, static_cast<size_t>(batch) + 1))) return rc;
     if ((rc = s.alloc(&partials, static_cast<size_t>(batch) * a.tiles * G::NV))) return rc;
     if (!single_launch) counters = nullptr;
-    else if (!s.arena) SEP_CUDA(cudaMemsetAsync(counters, 0, sizeof(int) * (batch + 1), stream));
+    else if ((rc = reset_counters(counters, batch, s, stream))) return rc;
   }
   a.partials = partials;
   a.counters = counters;

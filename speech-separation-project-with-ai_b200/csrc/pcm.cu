@@ -31,20 +31,34 @@ __global__ void pcm16_to_f32_kernel(const int16_t *__restrict__ pcm, int64_t n, 
 }
 
 // |x| as an unsigned integer is monotonic in |x| (NaN sorts above everything, like numpy's max propagates it)
-template <bool VEC>
-__global__ void row_absmax_kernel(const float *__restrict__ data, int64_t n, unsigned *__restrict__ rowmax) {
+template <typename T> struct AbsBits;
+template <> struct AbsBits<float> {
+  using U = unsigned;
+  static __device__ __forceinline__ U of(float v) { return __float_as_uint(v) & 0x7FFFFFFFu; }
+  static __device__ __forceinline__ float back(U u) { return __uint_as_float(u); }
+};
+template <> struct AbsBits<double> {
+  using U = unsigned long long;
+  static __device__ __forceinline__ U of(double v) { return static_cast<U>(__double_as_longlong(v)) & 0x7FFFFFFFFFFFFFFFull; }
+  static __device__ __forceinline__ double back(U u) { return __longlong_as_double(static_cast<long long>(u)); }
+};
+
+template <typename T, bool VEC>
+__global__ void row_absmax_kernel(const T *__restrict__ data, int64_t n, typename AbsBits<T>::U *__restrict__ rowmax) {
+  using B = AbsBits<T>;
   const int row = blockIdx.y;
-  const float *src = data + static_cast<int64_t>(row) * n;
-  unsigned m = 0;
-  constexpr int V = VEC ? 4 : 1;
+  const T *src = data + static_cast<int64_t>(row) * n;
+  typename B::U m = 0;
+  constexpr int V = VEC ? 16 / sizeof(T) : 1;
   for (int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * V; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x * V) {
     if (VEC) {
-      const float4 v = __ldg(reinterpret_cast<const float4 *>(src + i));
-      m = max(max(m, __float_as_uint(v.x) & 0x7FFFFFFFu), __float_as_uint(v.y) & 0x7FFFFFFFu);
-      m = max(max(m, __float_as_uint(v.z) & 0x7FFFFFFFu), __float_as_uint(v.w) & 0x7FFFFFFFu);
+      const float4 raw = __ldg(reinterpret_cast<const float4 *>(src + i));
+      const T *v = reinterpret_cast<const T *>(&raw);
+#pragma unroll
+      for (int k = 0; k < V; ++k) m = max(m, B::of(v[k]));
     } else {
-      m = max(m, __float_as_uint(__ldg(src + i)) & 0x7FFFFFFFu);
+      m = max(m, B::of(__ldg(src + i)));
     }
   }
 #pragma unroll
@@ -52,41 +66,48 @@ __global__ void row_absmax_kernel(const float *__restrict__ data, int64_t n, uns
   if ((threadIdx.x & 31) == 0 && m) atomicMax(rowmax + row, m);
 }
 
-__device__ __forceinline__ int16_t audiowrite_one(float v, bool norm, float peak, unsigned &over) {
-  if (norm) v = __fdiv_rn(v, peak);                  // data /= np.max(np.abs(data)), :1337
-  v = __fmul_rn(v, 32767.f);                         // data *= int16_max, :1340
-  over += v > 32767.f;                               // :1342
-  v = fminf(fmaxf(v, -32768.f), 32767.f);            // np.clip, :1345
+// One sample of cell 40 in the input's own precision (float32 data stays float32, float64 -- what the
+// reference's istft returns -- stays float64), numpy's order of operations.  NaN (an all-zero row
+// normalised by its zero peak, :1337) goes through np.clip unchanged and astype(np.int16) makes it 0.
+template <typename T>
+__device__ __forceinline__ int16_t audiowrite_one(T v, bool norm, T peak, unsigned &over) {
+  if (norm) v = v / peak;                            // data /= np.max(np.abs(data)), :1337 (IEEE division)
+  v = v * static_cast<T>(32767);                     // data *= int16_max, :1340
+  over += v > static_cast<T>(32767);                 // :1342
+  if (v != v) return 0;                              // NaN.astype(np.int16) == 0
+  v = v < static_cast<T>(-32768) ? static_cast<T>(-32768) : (v > static_cast<T>(32767) ? static_cast<T>(32767) : v);   // np.clip, :1345
   return static_cast<int16_t>(static_cast<int>(v));  // astype(np.int16): toward zero
 }
 
-// VEC: n % 8 == 0 and 16-byte aligned rows -> two float4 loads, one 16-byte store of eight int16
-template <bool VEC>
-__global__ void audiowrite_kernel(const float *__restrict__ data, int64_t n, const unsigned *__restrict__ rowmax,
+// VEC: n % 8 == 0 and 16-byte aligned rows -> 16-byte loads, one 16-byte store of eight int16
+template <typename T, bool VEC>
+__global__ void audiowrite_kernel(const T *__restrict__ data, int64_t n, const typename AbsBits<T>::U *__restrict__ rowmax,
                                   int16_t *__restrict__ out, unsigned long long *__restrict__ clipped) {
   const int row = blockIdx.y;
-  const float *src = data + static_cast<int64_t>(row) * n;
+  const T *src = data + static_cast<int64_t>(row) * n;
   int16_t *dst = out + static_cast<int64_t>(row) * n;
   const bool norm = rowmax != nullptr;
-  const float peak = norm ? __uint_as_float(rowmax[row]) : 1.f;
+  const T peak = norm ? AbsBits<T>::back(rowmax[row]) : static_cast<T>(1);
   unsigned over = 0;
   constexpr int V = VEC ? 8 : 1;
   for (int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * V; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x * V) {
     if (VEC) {
-      const float4 a = __ldg(reinterpret_cast<const float4 *>(src + i));
-      const float4 b = __ldg(reinterpret_cast<const float4 *>(src + i) + 1);
-      const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      constexpr int NL = 8 * sizeof(T) / 16;          // 16-byte loads for eight samples
+      float4 raw[NL];
+#pragma unroll
+      for (int k = 0; k < NL; ++k) raw[k] = __ldg(reinterpret_cast<const float4 *>(src + i) + k);
+      const T *v = reinterpret_cast<const T *>(raw);
       uint32_t w[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const uint32_t lo = static_cast<uint16_t>(audiowrite_one(v[2 * k], norm, peak, over));
-        const uint32_t hi = static_cast<uint16_t>(audiowrite_one(v[2 * k + 1], norm, peak, over));
+        const uint32_t lo = static_cast<uint16_t>(audiowrite_one<T>(v[2 * k], norm, peak, over));
+        const uint32_t hi = static_cast<uint16_t>(audiowrite_one<T>(v[2 * k + 1], norm, peak, over));
         w[k] = lo | (hi << 16);
       }
       *reinterpret_cast<uint4 *>(dst + i) = make_uint4(w[0], w[1], w[2], w[3]);
     } else {
-      dst[i] = audiowrite_one(__ldg(src + i), norm, peak, over);
+      dst[i] = audiowrite_one<T>(__ldg(src + i), norm, peak, over);
     }
   }
 #pragma unroll
@@ -118,18 +139,19 @@ extern "C" int sep_pcm16_to_f32(const int16_t *pcm, int64_t n, float *out, int m
   return finish(s, mem);
 }
 
-extern "C" int sep_audiowrite_i16_f32(const float *data, int batch, int64_t n, int normalize, int16_t *out,
-                                      int64_t *clipped, int mem, void *stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  SEP_REQUIRE(data && out && batch >= 1 && n >= 1, "sep_audiowrite_i16_f32: bad argument");
+template <typename T>
+static int audiowrite_impl(const T *data, int batch, int64_t n, int normalize, int16_t *out, int64_t *clipped, int mem,
+                           cudaStream_t stream) {
+  using U = typename AbsBits<T>::U;
+  SEP_REQUIRE(data && out && batch >= 1 && n >= 1, "sep_audiowrite_i16: bad argument");
   int rc = check_mem(mem);
   if (rc) return rc;
   Scratch s(stream);
   const size_t count = static_cast<size_t>(batch) * n;
-  const float *d_in;
+  const T *d_in;
   int16_t *d_out;
   unsigned long long *d_clip;
-  unsigned *d_max = nullptr;
+  U *d_max = nullptr;
   if ((rc = stage_in(s, data, count, mem, &d_in))) return rc;
   if ((rc = stage_out(s, out, count, mem, &d_out))) return rc;
   if ((rc = s.alloc(&d_clip, static_cast<size_t>(batch)))) return rc;
@@ -143,13 +165,13 @@ extern "C" int sep_audiowrite_i16_f32(const float *data, int batch, int64_t n, i
   profile_begin(stream);
   if (normalize) {
     if ((rc = s.alloc(&d_max, static_cast<size_t>(batch)))) return rc;
-    SEP_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned) * batch, stream));
-    if (vec) row_absmax_kernel<true><<<grid, 256, 0, stream>>>(d_in, n, d_max);
-    else row_absmax_kernel<false><<<grid, 256, 0, stream>>>(d_in, n, d_max);
+    SEP_CUDA(cudaMemsetAsync(d_max, 0, sizeof(U) * batch, stream));
+    if (vec) row_absmax_kernel<T, true><<<grid, 256, 0, stream>>>(d_in, n, d_max);
+    else row_absmax_kernel<T, false><<<grid, 256, 0, stream>>>(d_in, n, d_max);
     SEP_LAUNCHED();
   }
-  if (vec) audiowrite_kernel<true><<<grid, 256, 0, stream>>>(d_in, n, d_max, d_out, d_clip);
-  else audiowrite_kernel<false><<<grid, 256, 0, stream>>>(d_in, n, d_max, d_out, d_clip);
+  if (vec) audiowrite_kernel<T, true><<<grid, 256, 0, stream>>>(d_in, n, d_max, d_out, d_clip);
+  else audiowrite_kernel<T, false><<<grid, 256, 0, stream>>>(d_in, n, d_max, d_out, d_clip);
   profile_end(stream);
   SEP_LAUNCHED();
   if ((rc = copy_back(s, out, d_out, count, mem))) return rc;
@@ -162,4 +184,14 @@ extern "C" int sep_audiowrite_i16_f32(const float *data, int batch, int64_t n, i
     }
   }
   return finish(s, mem);
+}
+
+extern "C" int sep_audiowrite_i16_f32(const float *data, int batch, int64_t n, int normalize, int16_t *out,
+                                      int64_t *clipped, int mem, void *stream_) {
+  return audiowrite_impl<float>(data, batch, n, normalize, out, clipped, mem, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int sep_audiowrite_i16_f64(const double *data, int batch, int64_t n, int normalize, int16_t *out,
+                                      int64_t *clipped, int mem, void *stream_) {
+  return audiowrite_impl<double>(data, batch, n, normalize, out, clipped, mem, static_cast<cudaStream_t>(stream_));
 }

@@ -65,6 +65,7 @@ PROTOTYPES = {
                               _int, _vp]),
     "sep_pcm16_to_f32": (_int, [_vp, _i64, _vp, _int, _vp]),
     "sep_audiowrite_i16_f32": (_int, [_vp, _int, _i64, _int, _vp, _vp, _int, _vp]),
+    "sep_audiowrite_i16_f64": (_int, [_vp, _int, _i64, _int, _vp, _vp, _int, _vp]),
 }
 
 _lib = None

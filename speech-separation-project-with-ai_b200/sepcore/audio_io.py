@@ -37,15 +37,21 @@ def pcm16_to_float32(pcm, out=None):
 
 
 def audiowrite_int16(data, normalize=False, out=None, clipped=None):
-    """The sample conversion inside `audiowrite` (cell 40 :1331-1346) for float32 data [n] or [B, n]
+    """The sample conversion inside `audiowrite` (cell 40 :1331-1346) for data [n] or [B, n]
     (row by row): returns (int16 array, clipped count per row -- a Python int for 1-D input).
-    `out` / `clipped` (device mode): preallocated int16 [B, n] / int64 [B] CUDA tensors."""
+    The arithmetic runs in the input's own precision like numpy's: float32 stays float32,
+    float64 (what the reference's istft returns) stays float64; other float types are computed
+    in float32.  `out` / `clipped` (device mode): preallocated int16 [B, n] / int64 [B] CUDA tensors."""
     lib = _lib.load()
     dev = is_device_tensor(data)
     if dev:
         import torch
 
-        x = data if data.dtype == torch.float32 and data.is_contiguous() else data.float().contiguous()
+        if data.dtype == torch.float64:
+            x, fn = data.contiguous(), lib.sep_audiowrite_i16_f64
+        else:
+            x = data if data.dtype == torch.float32 and data.is_contiguous() else data.float().contiguous()
+            fn = lib.sep_audiowrite_i16_f32
         rows = x.reshape(1, -1) if x.dim() == 1 else x
         if out is None:
             out = torch.empty(rows.shape, dtype=torch.int16, device=x.device)
@@ -53,15 +59,19 @@ def audiowrite_int16(data, normalize=False, out=None, clipped=None):
             clipped = torch.empty((rows.shape[0],), dtype=torch.int64, device=x.device)
         mem, stream = _lib.MEM_DEVICE, current_stream(_lib.MEM_DEVICE, x)
     else:
-        x = as_f32_host(data)
+        x = np.asarray(data)
+        if x.dtype == np.float64:
+            x, fn = np.ascontiguousarray(x), lib.sep_audiowrite_i16_f64
+        else:
+            x, fn = as_f32_host(x), lib.sep_audiowrite_i16_f32
         rows = x.reshape(1, -1) if x.ndim == 1 else x
         out = np.empty(rows.shape, dtype=np.int16)
         clipped = np.empty((rows.shape[0],), dtype=np.int64)
         mem, stream = _lib.MEM_HOST, None
     if rows.ndim != 2 or rows.shape[1] < 1:
         raise ValueError("data must be [n] or [B, n] with n >= 1")
-    _lib.check(lib.sep_audiowrite_i16_f32(ptr(rows), int(rows.shape[0]), int(rows.shape[1]), int(bool(normalize)),
-                                          ptr(out), ptr(clipped), mem, stream), "sep_audiowrite_i16_f32")
+    _lib.check(fn(ptr(rows), int(rows.shape[0]), int(rows.shape[1]), int(bool(normalize)),
+                  ptr(out), ptr(clipped), mem, stream), "sep_audiowrite_i16")
     if (x.dim() if dev else x.ndim) == 1:
         return out.reshape(-1), int(clipped[0])
     return out, clipped
@@ -69,10 +79,24 @@ def audiowrite_int16(data, normalize=False, out=None, clipped=None):
 
 def audiowrite(data, path, samplerate=16000, normalize=False, threaded=True):
     """Reference signature (uPIT_baseline.ipynb:1317): converts on the GPU, writes the wav with
-    scipy (optionally on a thread, like the reference); returns the number of clipped samples."""
+    scipy (optionally on a thread, like the reference); returns the number of clipped samples.
+
+    Like the reference cell: the peak of `normalize` is the maximum over the WHOLE array (a
+    multi-channel [n, ch] array is normalised by one common peak and written with its shape);
+    float data is scaled by 32767, integer data is not (:1339-1340) -- with normalize it is first
+    promoted to float64 (:1335-1337), without it only clipped to the int16 range and cast."""
     from scipy.io.wavfile import write as wav_write
 
-    pcm, clipped = audiowrite_int16(np.asarray(data).reshape(-1), normalize)
+    arr = np.asarray(data)
+    if arr.dtype.kind != 'f' and not normalize:
+        # integer samples pass through: count, clip, cast -- a format step with no arithmetic to accelerate
+        clipped = int(np.sum(arr > np.iinfo(np.int16).max))
+        pcm = np.clip(arr, np.iinfo(np.int16).min, np.iinfo(np.int16).max).astype(np.int16)
+    else:
+        if arr.dtype.kind != 'f':
+            arr = arr.astype(np.float64)
+        pcm, clipped = audiowrite_int16(arr.reshape(-1), normalize)
+        pcm = pcm.reshape(arr.shape)
     if clipped > 0:
         print('Warning, clipping {} samples'.format(clipped))
     if threaded:

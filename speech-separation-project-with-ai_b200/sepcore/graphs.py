@@ -21,8 +21,11 @@ class GraphedSeparator:
     streams: independent steps are captured round-robin on this many streams (fork /
     join inside the graph), so the serial tail of one step (last tile -> utterance
     finalisation -> batch sums) and its last partial wave of CTAs overlap the next
-    step's main phase.  Needs streams <= len(buffer_sets): concurrent steps never
-    share buffers or workspaces.
+    step's main phase.  Concurrent steps must never share outputs or a workspace (the
+    in-kernel finalisation counters live there), so the number of streams actually used
+    is the largest divisor of len(buffer_sets) that is <= `streams`: step s runs on lane
+    s % n_streams with set s % len(buffer_sets), and because n_streams divides the number
+    of sets every set is only ever touched by one lane (stream order serialises its reuse).
     """
 
     def __init__(self, buffer_sets, steps, size=256, shift=128, window=None, want_est=True, streams=1):
@@ -57,7 +60,8 @@ class GraphedSeparator:
                 self._step(i, 0)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        self.n_streams = max(1, min(int(streams), len(buffer_sets), max(self.steps, 1)))
+        want = max(1, min(int(streams), len(buffer_sets), max(self.steps, 1)))
+        self.n_streams = max(d for d in range(1, want + 1) if len(buffer_sets) % d == 0)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             main = torch.cuda.current_stream(dev)

@@ -473,6 +473,154 @@ def test_fused_device_tensors_full_size(sep, oracle, key):
     assert rel_err(host["est"], est[:4]) < 1e-6
 
 
+def test_fused_cfg4_full_size(sep, oracle):
+    """BASELINE config 4 at full size: 64 x 8 s (64000 samples), three sources, Hann 512/128, ragged
+    frame_lengths -- the strip partition of the 512-point kernel depends on the batch shape, so the small
+    cases above do not cover this plan.  Utterances 0 / 31 / 63 against the oracle (permutation exact over the
+    6 assignments, SI-SDR within 0.01 dB) + size-independent properties on the whole batch."""
+    import torch
+    rng = np.random.default_rng(44)
+    cfg = CONFIGS["hann_512_128"]
+    batch, n, n_src = 64, 64000, 3
+    mix, refs, masks, lengths = _fused_case(rng, batch, n, n_src, cfg, oracle, ragged=True)
+    dm, dr, dk, dl = (torch.from_numpy(a).cuda() for a in (mix, refs, masks, lengths))
+    res = sep.separate_and_score(dm, dk, dr, frame_lengths=dl, **cfg)
+    torch.cuda.synchronize()
+    est = res["est"].cpu().numpy()
+    for b in (0, 31, 63):
+        want = oracle.separate_and_score(mix[b], refs[b], masks[b], length=lengths[b], **cfg)
+        assert rel_err(est[b], want["ests"][:, :n]) < TOL_REL
+        assert rel_l2(est[b], want["ests"][:, :n]) < 1e-5
+        pit = want["pit"]
+        assert int(res["pit_perm"][b].item()) == int(pit["idx"][0])          # one of 6 permutations, exact
+        assert np.allclose(res["pit_costs"][b].cpu().numpy(), pit["costs"][0], rtol=1e-4)
+        assert abs(res["pit_loss"][b].item() - pit["loss"]) < 1e-4 * abs(pit["loss"])
+        assert np.max(np.abs(res["si_pair"][b].cpu().numpy() - want["si_sdr_pair"])) < TOL_DB
+    # linearity over the whole batch: masks that sum to one -> the three estimates sum to the mixture
+    comp = dk.clone()
+    comp[:, 2] = 1.0 - comp[:, 0] - comp[:, 1]
+    both = sep.separate_and_score(dm, comp, None, **cfg)["est"].sum(dim=1).cpu().numpy()
+    assert rel_err(both, mix) < TOL_REL
+    sums = res["sums"].cpu().numpy()
+    assert abs(sums[0] - float(res["pit_loss"].sum().item())) < 1e-9 * abs(sums[0]) and sums[3] == batch
+
+
+def _cfg3_dataset(n_utts, seed_len=4, seed_sig=5):
+    """lengths 8000 * U[2, 10] s, refs 0.1 * N(0,1), est = ref + 10^(-snr/20) * noise with
+    snr ~ U[-5, 20] dB, every second utterance with the estimates swapped, estimate length off by up to 8000."""
+    rng_len, rng = np.random.default_rng(seed_len), np.random.default_rng(seed_sig)
+    lens = np.round(8000 * rng_len.uniform(2.0, 10.0, size=n_utts)).astype(np.int64)
+    quads = []
+    for i in range(n_utts):
+        n = int(lens[i])
+        ne = max(1, n + int(rng_len.integers(-4000, 4001)))
+        r = (0.1 * rng.standard_normal((2, n), dtype=np.float32))
+        snr = rng.uniform(-5.0, 20.0)
+        m = max(n, ne)
+        e = np.zeros((2, m), np.float32)
+        e[:, :n] = r
+        e += np.float32(10 ** (-snr / 20) * 0.1) * rng.standard_normal((2, m), dtype=np.float32)
+        e = e[:, :ne]
+        if i % 2:
+            e = e[::-1]
+        quads.append((r[0], r[1], np.ascontiguousarray(e[0]), np.ascontiguousarray(e[1])))
+    return quads
+
+
+def test_score_batch_cfg3_dataset(sep, oracle):
+    """BASELINE config 3: the seeded 3000-utterance wsj0-2mix-shaped set (ragged, estimate and reference
+    lengths differ -> truncate-to-min of evaluate_metrics.py:46-48, half of the estimates swapped) through
+    `score_batch` in one call: 60 sampled utterances and the dataset mean (float32, like eval_si_sdr :53)
+    against the oracle."""
+    quads = _cfg3_dataset(3000)
+    refs, ests = [], []
+    for q in quads:
+        r1, r2, e1, e2 = sep.truncate_to_min_len(*q)
+        refs.append([r1, r2])
+        ests.append([e1, e2])
+    res = sep.score_batch(refs, ests, 2)
+    sample = list(range(0, 3000, 50))
+    for b in sample:
+        v, p, _, _ = oracle.permute_si_sdr_detail(*oracle.truncate_to_min_len(*quads[b]))
+        assert int(res["si_perm"][b]) == p == b % 2
+        assert abs(float(res["si_best"][b]) - float(v)) < TOL_DB
+        v, p, _, _ = oracle.permute_sdr_detail(*oracle.truncate_to_min_len(*quads[b]))
+        assert abs(float(res["sdr_best"][b]) - float(v)) < TOL_DB
+    want_mean, values = oracle.eval_si_sdr_arrays(quads)
+    got_mean = np.mean(np.array([np.float32(v) for v in res["si_best"]]))
+    assert abs(float(got_mean) - float(want_mean)) < TOL_DB
+    assert np.max(np.abs(np.asarray(res["si_best"]) - np.asarray(values, np.float64))) < TOL_DB
+    assert np.array_equal(np.asarray(res["si_perm"]).astype(int), np.arange(3000) % 2)
+    assert abs(res["sums"][0] / res["sums"][2] - float(want_mean)) < TOL_DB and res["sums"][2] == 3000
+
+
+def test_si_sdr_tie_and_nan_rules(sep, oracle):
+    """evaluate_metrics.py:28-34: `if sdr1 > sdr2` -- an exact tie and a NaN sum both fall through to the
+    else branch (the CROSSED assignment); silence gives 0/0 = NaN (no epsilon, :22-26) and NaN propagates."""
+    rng = np.random.default_rng(77)
+    n = 20000
+    r = (0.1 * rng.standard_normal((2, n))).astype(np.float32)
+    e = (r + 0.05 * rng.standard_normal((2, n))).astype(np.float32)
+    zero = np.zeros(n, np.float32)
+    cases = {
+        "tie": ([r[0], r[1]], [e[0], e[0]]),            # both estimates identical: straight == crossed exactly
+        "silent_est": ([r[0], r[1]], [zero, e[1]]),     # SI(r, 0) = 0/0 -> both sums NaN -> crossed, NaN
+        "silent_ref": ([zero, r[1]], [e[0], e[1]]),     # |ref|^2 = 0 -> NaN
+        "all_silent": ([zero, zero], [zero, zero]),
+        "plain": ([r[0], r[1]], [e[0], e[1]]),
+    }
+    refs = [c[0] for c in cases.values()]
+    ests = [c[1] for c in cases.values()]
+    res = sep.score_batch(refs, ests, 2)
+    with np.errstate(all="ignore"):
+        for b, (name, (rr, ee)) in enumerate(cases.items()):
+            v, p, straight, crossed = oracle.permute_si_sdr_detail(rr[0], rr[1], ee[0], ee[1])
+            assert int(res["si_perm"][b]) == p, name
+            if np.isnan(v):
+                assert np.isnan(res["si_best"][b]), name
+            else:
+                assert abs(float(res["si_best"][b]) - float(v)) < TOL_DB, name
+            pair = res["si_pair"][b]
+            for (i, j) in ((0, 0), (0, 1), (1, 0), (1, 1)):
+                w = oracle.si_sdr(rr[j], ee[i])
+                assert (np.isnan(w) and np.isnan(pair[i, j])) or abs(float(pair[i, j]) - float(w)) < TOL_DB, (name, i, j)
+            # the drop-in function itself
+            got = sep.permute_si_sdr(rr[0], rr[1], ee[0], ee[1])
+            assert (np.isnan(v) and np.isnan(got)) or abs(float(got) - float(v)) < TOL_DB, name
+    assert int(res["si_perm"][0]) == 1 and res["si_pair"][0][0, 0] == res["si_pair"][0][1, 0]      # the tie is exact
+    assert [int(res["si_perm"][b]) for b in (1, 2, 3)] == [1, 1, 1] and int(res["si_perm"][4]) == 0
+    # the same rules inside the fused kernel's finalisation: two identical masks and identical references'
+    # roles swapped cannot be told apart -> SI-SDR tie -> crossed; PIT tie -> straight (strict `>`, cell 28 :1054)
+    cfg = CONFIGS["blackman_256_128"]
+    mix, refs4, masks, _ = _fused_case(rng, 2, 8000, 2, cfg, oracle)
+    masks[:, 1] = masks[:, 0]
+    out = sep.separate_and_score(mix, masks, refs4, **cfg)
+    assert np.array_equal(out["si_perm"], [1, 1]) and np.array_equal(out["pit_perm"], [0, 0])
+    assert np.array_equal(out["pit_costs"][:, 0], out["pit_costs"][:, 1])
+
+
+def test_cfg1_hann_est_vs_ref_scoring(sep, oracle, wsj0):
+    """BASELINE config 1 at its own parameterisation (Hann 256/64) beyond the round trip: the committed
+    mixtures through mask -> iSTFT with ideal-ratio-style masks, estimates scored against tt/s{1,2}; every
+    utterance against the oracle chain."""
+    cfg = CONFIGS["hann_256_64"]
+    for utt in wsj0:
+        n = min(len(utt["mix"]), len(utt["s1"]), len(utt["s2"]))
+        mix = utt["mix"][:n][None]
+        refs = np.stack([utt["s1"][:n], utt["s2"][:n]])[None]
+        s1 = np.abs(oracle.stft(refs[0, 0], time_dim=0, **cfg))
+        s2 = np.abs(oracle.stft(refs[0, 1], time_dim=0, **cfg))
+        irm = (s1 / np.maximum(s1 + s2, 1e-12)).astype(np.float32)
+        masks = np.stack([irm, 1.0 - irm])[None]
+        res = sep.separate_and_score(mix, masks, refs, **cfg)
+        want = oracle.separate_and_score(mix[0], refs[0], masks[0], **cfg)
+        assert rel_err(res["est"][0], want["ests"][:, :n]) < TOL_REL
+        assert int(res["pit_perm"][0]) == int(want["pit"]["idx"][0])
+        assert np.max(np.abs(res["si_pair"][0] - want["si_sdr_pair"])) < TOL_DB
+        v, p, _, _ = oracle.permute_si_sdr_detail(refs[0, 0], refs[0, 1], *want["ests"][:, :n].astype(np.float32))
+        assert int(res["si_perm"][0]) == p and abs(float(res["si_best"][0]) - float(v)) < TOL_DB
+
+
 # ----------------------------------------------------------------- a14 conv1d filterbank
 def test_conv1d_reference_shape(sep, oracle):
     """Raw_with_Convlayer: [B, K, 40] -> Conv1D(129, 2, sigmoid, 'same') (10449 params)."""
