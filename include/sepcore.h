@@ -62,6 +62,9 @@ const char *sep_last_error(void);
 /* Number of kernels this library has launched in the calling process so far
  * (all threads); bench.py reports the difference over the timed region. */
 int64_t     sep_launch_count(void);
+/* Name (with its template parameters) of the dominant kernel the last entry point called on this
+ * thread launched, e.g. "wstrip256_kernel<C=2,R=2,SCORE=1>"; bench.py prints it in `roofline.kernel`. */
+const char *sep_last_kernel(void);
 
 /* Per-kernel timing for bench.py's roofline leg: while enabled, entry points
  * bracket their dominant kernel with CUDA events on the launching stream (not

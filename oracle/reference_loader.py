@@ -3,8 +3,9 @@
 TEST INFRASTRUCTURE -- used by ``oracle/make_golden.py`` to generate the
 committed golden vectors and by the CPU tests (when the tree is present) to pin
 the numpy restatement in ``oracle/signal_path.py``.  The GPU box has no
-/root/reference: nothing in the ``-m gpu`` tests, ``smoke()`` or ``bench.py``
-calls this module.
+/root/reference: nothing in the ``-m gpu`` tests or ``smoke()`` calls this module;
+``bench.py --impl reference`` / ``cpu_baseline`` use it there through the copies in
+``oracle/_ref/`` (``oracle/build_ref.py``) to TIME the unmodified reference on the host cores.
 
 The reference modules import tensorflow / librosa / soundfile / museval at the
 top and use ``np.int``, ``scipy.signal.blackman`` and ``scipy.zeros``, all gone
@@ -21,7 +22,19 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("SEP_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _default_root():
+    """/root/reference in the authoring container; on the GPU box the byte-for-byte copies that
+    oracle/build_ref.py put under oracle/_ref/ (git-ignored, travels with the snapshot)."""
+    for root in (os.environ.get("SEP_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if root and os.path.isfile(os.path.join(root, "parallel_stft.py")):
+            return root
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _default_root()
 
 
 def available() -> bool:

@@ -35,7 +35,7 @@ extern std::atomic<int64_t> g_launches;
     }                                                                               \
   } while (0)
 
-void profile_begin(cudaStream_t stream);
+void profile_begin(cudaStream_t stream, const char *fmt = nullptr, ...);
 void profile_end(cudaStream_t stream);
 
 // counts one kernel launch and checks the launch error

@@ -120,8 +120,10 @@ extern "C" int sep_conv1d_f32(const float *x, const float *kernel, const float *
   const size_t n_out = static_cast<size_t>(batch) * rows_out * filters;
   if ((rc = stage_out(s, out, n_out, mem, &d_out))) return rc;
   dim3 grid((rows_out + kTM - 1) / kTM, (filters + kTN - 1) / kTN, batch);
+  profile_begin(stream, "conv1d_kernel (fp32 SIMT, 64x64 tiles; taps=%d c_in=%d filters=%d stride=%d)", taps, c_in, filters, stride);
   conv1d_kernel<<<grid, 256, 0, stream>>>(d_x, d_w, d_b, rows, c_in, taps, filters, stride, left,
                                           rows_out, activation, d_out);
+  profile_end(stream);
   SEP_LAUNCHED();
   if ((rc = copy_back(s, out, d_out, n_out, mem))) return rc;
   return finish(s, mem);

@@ -630,7 +630,7 @@ extern "C" int sep_filterbank_separate_f32(const float *wave, const float *enc, 
   dim3 grid(static_cast<unsigned>(std::min<int64_t>(static_cast<int64_t>(a.tiles) * batch, sms)));
   CUtensorMap mask_map;
   if ((rc = make_mask_map(&mask_map, a.masks, static_cast<uint64_t>(batch) * n_src * K))) return rc;
-  profile_begin(stream);
+  profile_begin(stream, "filterbank_kernel (tcgen05 kind::tf32 x3, TMEM, TMA; N=256 L=16 stride=8, C=%d)", n_src);
   filterbank_kernel<<<grid, kFbThreads, kFbSmem, stream>>>(a, mask_map);
   profile_end(stream);
   SEP_LAUNCHED();

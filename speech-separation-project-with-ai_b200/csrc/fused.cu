@@ -243,7 +243,7 @@ static int run_fused(const sep_plan *p, FusedArgs a, int batch, double *d_scores
                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(cfg.smem)));
   dim3 grid(a.tiles, batch);
-  profile_begin(stream);
+  profile_begin(stream, "fused_generic_kernel<C=%d> (size=%d shift=%d)", C, p->size, p->shift);
   fused_generic_kernel<C><<<grid, cfg.warps * 32, cfg.smem, stream>>>(a);
   profile_end(stream);
   SEP_LAUNCHED();

@@ -323,7 +323,7 @@ static int launch_fast(FusedArgs a, int batch, double *d_scores, double *d_sums,
   SEP_CUDA(cudaFuncSetAttribute(fused256_kernel<C, R, SCORE>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   dim3 grid(a.tiles, batch);
-  profile_begin(stream);
+  profile_begin(stream, "fused256_kernel<C=%d,R=%d,SCORE=%d>", C, R, int(SCORE));
   fused256_kernel<C, R, SCORE><<<grid, kFastThreads, smem, stream>>>(a);
   profile_end(stream);
   SEP_LAUNCHED();

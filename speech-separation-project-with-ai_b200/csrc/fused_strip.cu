@@ -434,7 +434,7 @@ static int launch_strip_w(const sep_plan *p, FusedArgs a, int batch, double *d_s
                                 static_cast<int>(smem)));
   const int64_t total = static_cast<int64_t>(batch) * a.tiles;
   const int grid = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(sms) * CTAS_PER_SM, (total + W - 1) / W));
-  profile_begin(stream);
+  profile_begin(stream, "strip256_kernel<C=%d,R=%d,SCORE=%d,W=%d>", C, R, int(SCORE), W);
   strip256_kernel<C, R, SCORE, W, CTAS_PER_SM><<<grid, W * 32, smem, stream>>>(a);
   profile_end(stream);
   SEP_LAUNCHED();

@@ -447,7 +447,7 @@ static int launch_strip512(const sep_plan *p, FusedArgs a, int batch, double *d_
                                 static_cast<int>(smem)));
   const int64_t total = static_cast<int64_t>(batch) * a.tiles;
   const int grid = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(sms) * CTAS_PER_SM, (total + W - 1) / W));
-  profile_begin(stream);
+  profile_begin(stream, "strip512_kernel<C=%d,SCORE=%d,W=%d>", C, int(SCORE), W);
   strip512_kernel<C, SCORE, W><<<grid, W * 32, smem, stream>>>(a);
   profile_end(stream);
   SEP_LAUNCHED();

@@ -534,7 +534,7 @@ static int launch_wstrip_w(const sep_plan *p, FusedArgs a, int batch, double *d_
                                 static_cast<int>(smem)));
   const int64_t total = static_cast<int64_t>(batch) * a.tiles;
   const int grid = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(sms) * CPS, (total + W - 1) / W));
-  profile_begin(stream);
+  profile_begin(stream, "wstrip256_kernel<C=%d,R=%d,SCORE=%d,W=%d,CTAS_PER_SM=%d>", C, R, int(SCORE), W, CPS);
   wstrip256_kernel<C, R, SCORE, W, CPS, DUAL><<<grid, W * 32, smem, stream>>>(a);
   profile_end(stream);
   SEP_LAUNCHED();

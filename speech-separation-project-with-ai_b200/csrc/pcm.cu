@@ -131,7 +131,7 @@ extern "C" int sep_pcm16_to_f32(const int16_t *pcm, int64_t n, float *out, int m
   if ((rc = stage_in(s, pcm, static_cast<size_t>(n), mem, &d_in))) return rc;
   if ((rc = stage_out(s, out, static_cast<size_t>(n), mem, &d_out))) return rc;
   const int64_t threads = (n + 7) / 8;
-  profile_begin(stream);
+  profile_begin(stream, "pcm16_to_f32_kernel");
   pcm16_to_f32_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(d_in, n, d_out);
   profile_end(stream);
   SEP_LAUNCHED();
@@ -162,7 +162,7 @@ static int audiowrite_impl(const T *data, int batch, int64_t n, int normalize, i
   const unsigned bx = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((n + per_block - 1) / per_block,
                                                                              (148 * 32 + batch - 1) / batch)));
   const dim3 grid(bx, batch);
-  profile_begin(stream);
+  profile_begin(stream, "row_absmax_kernel + audiowrite_kernel<%s>", sizeof(T) == 4 ? "float" : "double");
   if (normalize) {
     if ((rc = s.alloc(&d_max, static_cast<size_t>(batch)))) return rc;
     SEP_CUDA(cudaMemsetAsync(d_max, 0, sizeof(U) * batch, stream));

@@ -136,7 +136,9 @@ static int run_pit(const float *d_true, const float *d_pred, int batch, int T, i
   int rc;
   if ((rc = s.alloc(&partials, static_cast<size_t>(batch) * chunks * C * C))) return rc;
   if ((rc = s.alloc(&rows, static_cast<size_t>(batch) * (C * C + P + 2)))) return rc;
+  profile_begin(stream, "pit_pair_kernel<C=%d>", C);
   pit_pair_kernel<C><<<dim3(chunks, batch), 256, 0, stream>>>(d_true, d_pred, T, F, chunks, partials);
+  profile_end(stream);
   SEP_LAUNCHED();
   pit_finalize_kernel<C><<<batch, 32, 0, stream>>>(partials, chunks, d_true, T, C * F, rows);
   SEP_LAUNCHED();

@@ -39,7 +39,16 @@ static void profile_mark(cudaStream_t stream) {
   }
   cudaEventRecord(g_prof_events[g_prof_used++], stream);
 }
-void profile_begin(cudaStream_t stream) { profile_mark(stream); }
+static thread_local char t_kernel[160] = "";
+void profile_begin(cudaStream_t stream, const char *fmt, ...) {
+  if (fmt) {                                     // name of the dominant kernel this entry point is about to launch
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_kernel, sizeof(t_kernel), fmt, ap);
+    va_end(ap);
+  }
+  profile_mark(stream);
+}
 void profile_end(cudaStream_t stream) { profile_mark(stream); }
 
 template <typename T>
@@ -58,6 +67,8 @@ extern "C" {
 int sep_version(void) { return 100; }
 
 const char *sep_last_error(void) { return t_error.c_str(); }
+
+const char *sep_last_kernel(void) { return t_kernel; }
 
 int64_t sep_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

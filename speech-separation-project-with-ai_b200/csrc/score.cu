@@ -172,7 +172,7 @@ static int run_score(const float *d_refs, const float *d_ests, const int64_t *d_
   int rc;
   if ((rc = s.alloc(&partials, static_cast<size_t>(items) * NV))) return rc;
   if (items > 0) {
-    profile_begin(stream);
+    profile_begin(stream, "score_chunk_kernel<C=%d>", C);
     score_chunk_kernel<C><<<items, kScoreThreads, 0, stream>>>(d_refs, d_ests, d_roff, d_eoff, d_len,
                                                                d_start, batch, partials);
     profile_end(stream);

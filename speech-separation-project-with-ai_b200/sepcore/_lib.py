@@ -37,6 +37,7 @@ PROTOTYPES = {
     "sep_version": (_int, []),
     "sep_last_error": (C.c_char_p, []),
     "sep_launch_count": (_i64, []),
+    "sep_last_kernel": (C.c_char_p, []),
     "sep_profile_enable": (_int, [_int]),
     "sep_profile_collect": (_int, [_f64p, C.POINTER(_int)]),
     "sep_plan_create": (_int, [C.POINTER(_vp), _int, _int, _f64p, _int]),
@@ -105,6 +106,11 @@ def check(rc, what=""):
 
 def launch_count():
     return int(load().sep_launch_count())
+
+
+def last_kernel():
+    """Name of the dominant kernel launched by the last library call on this thread."""
+    return load().sep_last_kernel().decode(errors="replace")
 
 
 def profile_enable(on=True):

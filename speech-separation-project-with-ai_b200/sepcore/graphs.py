@@ -26,9 +26,15 @@ class GraphedSeparator:
     is the largest divisor of len(buffer_sets) that is <= `streams`: step s runs on lane
     s % n_streams with set s % len(buffer_sets), and because n_streams divides the number
     of sets every set is only ever touched by one lane (stream order serialises its reuse).
+    reduce_each_step: None, or a callable `f(sums_row)` that all-reduces one step's
+    [loss, SI-SDR, SDR, n] row in place (e.g. `sepcore.distributed.all_reduce_sums`).  It is
+    captured into the graph on ONE dedicated communication stream, in step order -- the same
+    total order on every rank, as NCCL requires -- waiting only on the step that produced the
+    row, so the compute lanes never wait for the collective (per-batch all-reduce).
     """
 
-    def __init__(self, buffer_sets, steps, size=256, shift=128, window=None, want_est=True, streams=1):
+    def __init__(self, buffer_sets, steps, size=256, shift=128, window=None, want_est=True, streams=1,
+                 reduce_each_step=None):
         import torch
 
         self.sets = buffer_sets
@@ -65,17 +71,25 @@ class GraphedSeparator:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             main = torch.cuda.current_stream(dev)
-            if self.n_streams == 1:
+            if self.n_streams == 1 and reduce_each_step is None:
                 for s in range(self.steps):
                     self._step(s % len(buffer_sets), s)
             else:
                 lanes = [torch.cuda.Stream(device=dev) for _ in range(self.n_streams)]
-                for lane in lanes:                       # fork
+                comm = torch.cuda.Stream(device=dev) if reduce_each_step is not None else None
+                for lane in lanes + ([comm] if comm is not None else []):   # fork
                     lane.wait_stream(main)
                 for s in range(self.steps):
-                    with torch.cuda.stream(lanes[s % self.n_streams]):
+                    lane = lanes[s % self.n_streams]
+                    with torch.cuda.stream(lane):
                         self._step(s % len(buffer_sets), s)
-                for lane in lanes:                       # join
+                    if comm is not None and self.sums is not None:
+                        done = torch.cuda.Event()
+                        done.record(lane)
+                        with torch.cuda.stream(comm):
+                            comm.wait_event(done)
+                            reduce_each_step(self.sums[s])
+                for lane in lanes + ([comm] if comm is not None else []):   # join
                     main.wait_stream(lane)
 
     def _step(self, i, s):

@@ -28,16 +28,22 @@ class HostPipeline:
     as int16 PCM (decoded on the device exactly like wavread / librosa.load do: x / 32768), the
     estimates as the int16 samples `audiowrite(wav, path, rate, normalize=True)` would write
     (uPIT_baseline.ipynb:1403-1404), plus the per-row clipped counts: half the waveform bytes each way.
+
+    device_masks=True: `masks` given to submit() is a CUDA tensor that is already on the device -- in the
+    reference's pipeline the masks are the model's output (cell 29: `Multiply()([pred, inputs])`), produced
+    where they are consumed, so only the waveforms cross PCIe.  The tensor is read in place on the compute
+    stream (the caller's producer stream must have finished writing it, e.g. via torch's stream ordering).
     """
 
     def __init__(self, batch, n_src, n_samples, size=256, shift=128, window=None, depth=3,
-                 scored=True, want_est=True, device=None, pcm16=False):
+                 scored=True, want_est=True, device=None, pcm16=False, device_masks=False):
         import torch
 
         self.torch = torch
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
         self.kw = dict(size=size, shift=shift, window=window, want_est=want_est)
         self.scored, self.want_est, self.depth, self.pcm16 = scored, want_est, int(depth), bool(pcm16)
+        self.device_masks = bool(device_masks)
         from .plan import get_plan
 
         plan = get_plan(size, shift, window, True)
@@ -50,7 +56,7 @@ class HostPipeline:
         for _ in range(self.depth):
             s = {
                 "mix": torch.empty((batch, n_samples), **f32),
-                "masks": torch.empty((batch, n_src, frames, bins), **f32),
+                "masks": None if self.device_masks else torch.empty((batch, n_src, frames, bins), **f32),
                 "refs": torch.empty((batch, n_src, n_samples), **f32) if scored else None,
                 "workspace": torch.zeros(nbytes, dtype=torch.uint8, device=self.dev),
                 "out": {}, "host": {},
@@ -81,7 +87,8 @@ class HostPipeline:
         self.s_out = torch.cuda.Stream(device=self.dev)
         self.count = 0
         wave_bytes = 2 if self.pcm16 else 4
-        self.h2d_bytes = self.slots[0]["mix"].numel() * wave_bytes + self.slots[0]["masks"].numel() * 4 \
+        self.h2d_bytes = self.slots[0]["mix"].numel() * wave_bytes \
+            + (0 if self.device_masks else self.slots[0]["masks"].numel() * 4) \
             + (self.slots[0]["refs"].numel() * wave_bytes if scored else 0)
         self.d2h_bytes = sum(v.numel() * v.element_size() for v in self.slots[0]["host"].values())
 
@@ -97,7 +104,12 @@ class HostPipeline:
         slot["busy"] = True
         with torch.cuda.stream(self.s_in):
             slot["mix_i16" if self.pcm16 else "mix"].copy_(self._as_tensor(mix), non_blocking=True)
-            slot["masks"].copy_(self._as_tensor(masks), non_blocking=True)
+            if self.device_masks:
+                if not masks.is_cuda:
+                    raise ValueError("device_masks=True: masks must be a CUDA tensor")
+                slot["masks"] = masks
+            else:
+                slot["masks"].copy_(self._as_tensor(masks), non_blocking=True)
             if self.scored:
                 slot["refs_i16" if self.pcm16 else "refs"].copy_(self._as_tensor(refs), non_blocking=True)
             slot["ev_in"].record(self.s_in)
