@@ -246,6 +246,28 @@ int sep_audiowrite_i16_f32(const float *data, int batch, int64_t n, int normaliz
 int sep_audiowrite_i16_f64(const double *data, int batch, int64_t n, int normalize, int16_t *out,
                            int64_t *clipped, int mem, void *stream);
 
+/* ---- BSS Eval v4 ---- */
+/* museval.metrics.bss_eval(reference, estimated, window=np.inf, hop=np.inf, compute_permutation=True) as
+ * eval_sdr calls it (metrics/evaluate_metrics.py:79-81): one window, `filters_len`-tap time-invariant distortion
+ * filters (museval default 512), images criteria, single-channel signals.  Ragged batch in the layout of
+ * sep_score_batch_f32 (flat signals, HOST offset / length arrays).  rows[b] holds sep_bss_eval_row_width(C) =
+ * 4 C^2 + 2 + C float64 values:
+ *   [0, C^2)        SDR[jtrue][jest]   = 10 log10 |s|^2 / |e - s|^2
+ *   [C^2, 2C^2)     ISR[jtrue][jest]   = |s|^2 / |P_j e - s|^2
+ *   [2C^2, 3C^2)    SIR[jtrue][jest]   = |P_j e|^2 / |P_all e - P_j e|^2
+ *   [3C^2, 4C^2)    SAR[jtrue][jest]   = |P_all e|^2 / |e - P_all e|^2     (P: projection on the delayed references)
+ *   4C^2            index of the permutation with the largest mean SIR (itertools.permutations order, numpy argmax
+ *                   semantics; perm[jtrue] = jest)
+ *   4C^2 + 1        mean SDR of that assignment with eval_sdr's NaN fallback (:83-86: mean of nan_to_num)
+ *   4C^2 + 2 ..     SDR[jtrue][perm[jtrue]]
+ * A silent (all-zero) reference or estimate makes every criterion NaN like museval.  float64 arithmetic on the
+ * device; filters_len must be a multiple of 128 in [128, 1024].  PARITY UNPINNED against museval (not installable). */
+int sep_bss_eval_row_width(int n_src);
+int sep_bss_eval_f32(const float *refs, const float *ests, const int64_t *ref_offsets,
+                     const int64_t *est_offsets, const int64_t *lengths, int batch, int n_src,
+                     int64_t total_ref, int64_t total_est, int filters_len, double *rows, int mem,
+                     void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,11 +50,17 @@ def eval_si_sdr(wav_dir, test_dir):
 
 
 def eval_sdr(wav_dir, test_dir):
-    """Mean over files of the mean image-SDR of the best assignment
-    (evaluate_metrics.py:57-92).  The reference calls museval.metrics.bss_eval
-    (third party, not vendored): SDR values follow its published definition,
-    the permutation is chosen by mean SDR rather than museval's SIR --
-    parity unpinned."""
+    """Mean over files of the mean SDR of the assignment museval selects (evaluate_metrics.py:57-92).
+    The reference calls museval.metrics.bss_eval(reference, estimated, window=np.inf, hop=np.inf,
+    compute_permutation=True): BSS Eval v4 image criteria with 512-tap time-invariant distortion filters,
+    the permutation chosen by mean SIR, NaN fallback `np.mean(np.nan_to_num(sdr))` (:83-86).  Here the
+    whole directory is one batched GPU call (sepcore.bss_eval_batch -> sep_bss_eval_f32).
+
+    museval is third party and not installable in this stack: the CUDA path is checked against a float64
+    restatement of museval's published algorithm (oracle/bss_eval.py) -- parity with museval itself is
+    UNPINNED."""
+    from sepcore.bss import bss_eval_batch
+
     refs, ests = _load_pairs(wav_dir, test_dir)
-    res = score_batch(refs, ests, 2)
-    return np.mean(np.array(res["sdr_best"]))
+    res = bss_eval_batch(refs, ests, 2)
+    return np.mean(np.array(res["value"]))

@@ -38,6 +38,8 @@ PROTOTYPES = {
     "sep_last_error": (C.c_char_p, []),
     "sep_launch_count": (_i64, []),
     "sep_last_kernel": (C.c_char_p, []),
+    "sep_bss_eval_row_width": (_int, [_int]),
+    "sep_bss_eval_f32": (_int, [_vp, _vp, _i64p, _i64p, _i64p, _int, _int, _i64, _i64, _int, _vp, _int, _vp]),
     "sep_profile_enable": (_int, [_int]),
     "sep_profile_collect": (_int, [_f64p, C.POINTER(_int)]),
     "sep_plan_create": (_int, [C.POINTER(_vp), _int, _int, _f64p, _int]),
