@@ -110,8 +110,8 @@ class Workload:
                 "shift": self.shift, "window": self.window,
                 "l2": "inputs larger than L2: %d distinct buffer sets rotated (%.0f MB > 126 MB L2)"
                       % (self.n_sets, self.n_sets * self.bytes_per_launch / 1e6),
-                "replays": "a CUDA graph of --steps steps is replayed until the timed region is >= %g ms "
-                           "(count in timing.replays); ms_per_step = timed region / (replays * steps)" % MIN_TIMED_MS}
+                "replays": "the timed region holds timing.replays x --steps steps (>= %g ms), captured back to back in "
+                           "CUDA graphs of up to 1024 steps; ms_per_step = timed region / (replays * steps)" % MIN_TIMED_MS}
 
     def make_set(self, seed):
         """Synthetic wsj0-2mix-shaped batch: refs 0.1*N(0,1), mix = sum, masks U[0,1)."""
@@ -392,29 +392,51 @@ def measure_fused(ctx, wl, steps, warmup, streams, reduce_mode="bucket", alone_l
         dev_sets = [{k: torch.from_numpy(v).to(ctx.dev) for k, v in wl.make_set(1000 * ctx.rank + i).items()}
                     for i in range(wl.n_sets)]
     torch.cuda.synchronize()
-    block = min(steps, 1024)
-    n_blocks, tail = divmod(steps, block)
     per_batch = reduce_mode == "per_batch" and ctx.world > 1
     red = sepcore.distributed.all_reduce_sums if per_batch else None
-    graph = sepcore.GraphedSeparator(dev_sets, block, streams=streams, reduce_each_step=red, **kw)
-    tail_graph = sepcore.GraphedSeparator(dev_sets, tail, streams=streams, reduce_each_step=red, **kw) if tail else None
     warm = sepcore.GraphedSeparator(dev_sets, max(warmup, 3), streams=streams, **kw)
     warm.replay()
     if ctx.world > 1:
         dist.all_reduce(warm.sums)           # warms NCCL up too
-
-    def once():
-        for _ in range(n_blocks):
-            graph.replay()
-            if ctx.world > 1 and not per_batch:
-                dist.all_reduce(graph.sums)  # per-batch sums, one bucket per replay
-        if tail_graph is not None:
-            tail_graph.replay()
-            if ctx.world > 1 and not per_batch:
-                dist.all_reduce(tail_graph.sums)
-
-    ms_total, reps, clocks = timed_replays(ctx, once)
-    ms_step = ms_total / (reps * steps)
+    # The timed region must be >= MIN_TIMED_MS whatever --steps is (a 20-step graph is 0.5 ms: mostly ramp and
+    # tail of 50 us launches).  Estimate the step time on the warm-up graph, then time `reps` x --steps steps,
+    # captured back to back in graphs of up to 1024 steps (no join between the --steps groups).
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.barrier()
+    start.record()
+    for _ in range(4):
+        warm.replay()
+    stop.record()
+    torch.cuda.synchronize()
+    est_step = ctx.max_over_ranks(start.elapsed_time(stop) / (4 * warm.steps))
+    reps = max(1, int(math.ceil(MIN_TIMED_MS / max(est_step * steps, 1e-3))))
+    total_steps = reps * steps
+    block = min(total_steps, 1024)
+    n_blocks, tail = divmod(total_steps, block)
+    graph = sepcore.GraphedSeparator(dev_sets, block, streams=streams, reduce_each_step=red, **kw)
+    tail_graph = sepcore.GraphedSeparator(dev_sets, tail, streams=streams, reduce_each_step=red, **kw) if tail else None
+    graph.replay()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(ctx.local)
+    sampler.start()
+    ctx.barrier()
+    ctx.rendezvous()
+    start.record()
+    for _ in range(n_blocks):
+        graph.replay()
+        if ctx.world > 1 and not per_batch:
+            dist.all_reduce(graph.sums)      # per-batch sums, one bucket per replay
+    if tail_graph is not None:
+        tail_graph.replay()
+        if ctx.world > 1 and not per_batch:
+            dist.all_reduce(tail_graph.sums)
+    stop.record()
+    torch.cuda.synchronize()
+    ms_total = start.elapsed_time(stop)
+    clocks = sampler.summary()
+    ctx.barrier()
+    ms_total = ctx.max_over_ranks(ms_total)
+    ms_step = ms_total / total_steps
     sums = graph.sums[0].cpu().numpy().tolist()
 
     # the dominant kernel alone: eager launches, one at a time, bracketed by events in the library
@@ -446,7 +468,7 @@ def measure_fused(ctx, wl, steps, warmup, streams, reduce_mode="bucket", alone_l
         "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
         "traffic": traffic_for("%d_%d_c%d_b%d" % (wl.size, wl.shift, wl.sources, wl.batch)),
         "peak_source": peak_src, "kernel": kernel, "bytes_per_launch": wl.bytes_per_launch,
-        "launches_timed": reps * steps,
+        "launches_timed": total_steps,
         # achieved = algorithmic bytes per launch / (timed region / launches): the loop figure.  It is a
         # throughput inverse, NOT a launch duration: the graph keeps several launches in flight (one per stream)
         # and 2-3 of them are co-resident on an SM, which is how a stream of independent batches is meant to run.
@@ -458,6 +480,7 @@ def measure_fused(ctx, wl, steps, warmup, streams, reduce_mode="bucket", alone_l
     }
     return {"ms_total": ms_total, "replays": reps, "ms_per_step": ms_step, "clocks": clocks, "sums": sums,
             "launches_per_step": launches_per_step, "roofline": roofline, "graph_steps": block,
+            "graph_replays": n_blocks + (1 if tail else 0),
             "n_streams": graph.n_streams, "dev_sets": dev_sets,
             "value": ctx.world * wl.batch * wl.seconds / (ms_step * 1e-3)}
 
@@ -467,8 +490,8 @@ def fused_extra(ctx, name, wl, steps, streams):
     cfg = wl.config()
     return {"name": name, "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": ctx.world,
             "ms_per_step": r["ms_per_step"], "dtype": "f32", "scaling": "weak", "config": cfg,
-            "timing": {"replays": r["replays"], "graph_steps": r["graph_steps"], "timed_ms": r["ms_total"],
-                       "streams": r["n_streams"]},
+            "timing": {"replays": r["replays"], "steps_timed": r["replays"] * steps, "graph_steps": r["graph_steps"],
+                       "graph_replays": r["graph_replays"], "timed_ms": r["ms_total"], "streams": r["n_streams"]},
             "roofline": r["roofline"], "clocks": r["clocks"], "gpu_launches": r["launches_per_step"] * r["replays"] * steps,
             "check": {"pit_loss_sum": r["sums"][0], "si_sdr_sum": r["sums"][1], "n": r["sums"][3]}}
 
@@ -801,10 +824,11 @@ def run_sepcore(args):
             "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": wl.config(),
-            "timing": {"replays": r["replays"], "graph_steps": r["graph_steps"], "timed_ms": r["ms_total"],
-                       "streams": r["n_streams"],
-                       "launch": "CUDA graph replay (%d-step graphs, independent steps round-robin on %d streams inside "
-                                 "the graph), %d replays in the timed region" % (r["graph_steps"], r["n_streams"], r["replays"]),
+            "timing": {"replays": r["replays"], "steps_timed": r["replays"] * args.steps, "graph_steps": r["graph_steps"],
+                       "graph_replays": r["graph_replays"], "timed_ms": r["ms_total"], "streams": r["n_streams"],
+                       "launch": "%d x --steps = %d steps timed, captured in CUDA graphs of %d steps (independent steps "
+                                 "round-robin on %d streams inside a graph)"
+                                 % (r["replays"], r["replays"] * args.steps, r["graph_steps"], r["n_streams"]),
                        "parallelism": "utterance-sharded x%d, all-reduce of per-batch sums bucketed per replay "
                                       "(per-batch variant: extra.cfg2_per_batch_allreduce)" % ctx.world},
             "roofline": r["roofline"],

@@ -246,6 +246,22 @@ int sep_audiowrite_i16_f32(const float *data, int batch, int64_t n, int normaliz
 int sep_audiowrite_i16_f64(const double *data, int batch, int64_t n, int normalize, int16_t *out,
                            int64_t *clipped, int mem, void *stream);
 
+/* ---- feature / label records ---- */
+/* The record the reference writes for every utterance: make_sequence_example(inputs, labels, length, name)
+ * (parallel_stft_single.py:238-254, parallel_stft.py:217-229) serialised and framed by tf.io.TFRecordWriter
+ * (:287-309): a tf.train.SequenceExample with feature lists 'inputs' [frames x width_inputs float32],
+ * 'labels' [frames x width_labels], 'length' [1 float], 'name' [utf-8 bytes], inside the TFRecord framing
+ * (u64 length, masked CRC-32C, payload, masked CRC-32C).  Host buffers only (byte formatting, no kernel); the
+ * arrays are what sep_stft_features_f32 returns.  key_order: NULL (inputs, labels, length, name) or a permutation
+ * of {0: inputs, 1: labels, 2: length, 3: name} -- protobuf leaves the order of map entries open and the
+ * reference's committed files differ in it.  Byte-exact against those files (tests/test_records.py). */
+/* TFRecord's masked CRC-32C of a byte string (frames payloads that were serialised elsewhere). */
+uint32_t sep_record_masked_crc(const uint8_t *data, int64_t n);
+int sep_record_size(int frames, int width_inputs, int width_labels, int name_len, int64_t *bytes);
+int sep_record_encode(const float *inputs, const float *labels, int frames, int width_inputs,
+                      int width_labels, float length, const char *name, int name_len,
+                      const int *key_order, uint8_t *out, int64_t capacity, int64_t *written);
+
 /* ---- BSS Eval v4 ---- */
 /* museval.metrics.bss_eval(reference, estimated, window=np.inf, hop=np.inf, compute_permutation=True) as
  * eval_sdr calls it (metrics/evaluate_metrics.py:79-81): one window, `filters_len`-tap time-invariant distortion

@@ -75,10 +75,13 @@ def _reshape_G(G):
 
 
 def compute_projection_filters(G, sf, estimated_source):
-    """Least-squares projection of one estimate [nsampl, nchan] on the delayed references (delays 0..L-1)."""
+    """Least-squares projection of one estimate [nsampl, nchan] on the delayed references (delays 0..L-1).
+    G [nsrc, nsrc, nchan, nchan, L, L] -> C [nsrc, nchan, L, nchan]; G [nchan, nchan, L, L] (one reference
+    source, museval's G[jtrue, jtrue]) -> C [nchan, L, nchan]."""
     eps = np.finfo(float).eps
     nsampl, nchan = estimated_source.shape
-    if G.ndim == 4:                                                  # a single reference source
+    single = G.ndim == 4
+    if single:                                                       # a single reference source
         G = G[None, None, ...]
         sf = sf[None, ...]
     nsrc = G.shape[0]
@@ -97,7 +100,7 @@ def compute_projection_filters(G, sf, estimated_source):
     except np.linalg.LinAlgError:
         C = np.linalg.lstsq(Gm, D, rcond=None)[0]
     C = C.reshape(nsrc, nchan, filters_len, nchan)
-    return C[0] if nsrc == 1 else C
+    return C[0] if single else C
 
 
 def _project(reference_sources, C):

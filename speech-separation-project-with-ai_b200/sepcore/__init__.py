@@ -17,6 +17,7 @@ from .scoring import (permute_si_sdr, pow_norm, pow_np_norm, score_batch, score_
 from .filterbank import conv1d, filterbank_separate, segment_raw
 from .fused import parse_scores, score_layout, separate_and_score, workspace_bytes
 from .bss import bss_eval, bss_eval_batch
+from .records import SequenceExample, TFRecordWriter, gen_feats_record, make_sequence_example
 from .audio_io import audiowrite, audiowrite_int16, pcm16_to_float32
 from .tf_metrics import SiSdr, custom_sisdr_loss, sisdr_values
 from .graphs import GraphedSeparator
@@ -33,4 +34,5 @@ __all__ = [
     "separate_and_score", "score_layout", "parse_scores", "workspace_bytes", "GraphedSeparator", "HostPipeline",
     "audiowrite", "audiowrite_int16", "pcm16_to_float32", "SiSdr", "custom_sisdr_loss", "sisdr_values",
     "distributed", "bss_eval", "bss_eval_batch",
+    "SequenceExample", "TFRecordWriter", "gen_feats_record", "make_sequence_example",
 ]

@@ -38,6 +38,10 @@ PROTOTYPES = {
     "sep_last_error": (C.c_char_p, []),
     "sep_launch_count": (_i64, []),
     "sep_last_kernel": (C.c_char_p, []),
+    "sep_record_masked_crc": (C.c_uint32, [C.c_char_p, _i64]),
+    "sep_record_size": (_int, [_int, _int, _int, _int, C.POINTER(_i64)]),
+    "sep_record_encode": (_int, [_vp, _vp, _int, _int, _int, C.c_float, C.c_char_p, _int, _i32p, _vp, _i64,
+                                 C.POINTER(_i64)]),
     "sep_bss_eval_row_width": (_int, [_int]),
     "sep_bss_eval_f32": (_int, [_vp, _vp, _i64p, _i64p, _i64p, _int, _int, _i64, _i64, _int, _vp, _int, _vp]),
     "sep_profile_enable": (_int, [_int]),
