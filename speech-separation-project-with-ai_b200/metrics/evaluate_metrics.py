@@ -57,7 +57,7 @@ def eval_sdr(wav_dir, test_dir):
     whole directory is one batched GPU call (sepcore.bss_eval_batch -> sep_bss_eval_f32).
 
     museval is third party and not installable in this stack: the CUDA path is checked against a float64
-    restatement of museval's published algorithm (oracle/bss_eval.py) -- parity with museval itself is
+    restatement of museval's published algorithm (the test-side CPU checker) -- parity with museval itself is
     UNPINNED."""
     from sepcore.bss import bss_eval_batch
 

@@ -5,7 +5,7 @@ Reference call site: metrics/evaluate_metrics.py:79-81
                              compute_permutation=True)
 museval is a third-party dependency of the reference that is neither vendored nor installable here, so
 parity with museval itself is UNPINNED; the CUDA path is checked against a float64 restatement of museval's
-published algorithm (oracle/bss_eval.py).  See csrc/bss.cu for how the criteria are computed without ever
+published algorithm (the test-side CPU checker).  See csrc/bss.cu for how the criteria are computed without ever
 forming the 512-tap projections in the time domain.
 """
 from __future__ import annotations
