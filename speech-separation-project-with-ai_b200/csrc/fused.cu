@@ -335,6 +335,7 @@ extern "C" int sep_fused_separate_ws_f32(const sep_plan *p, const float *mix, co
   bool handled = false;
   if ((rc = fused_wstrip_try(p, a, batch, C, d_scores, d_sums, s, stream, &handled))) return rc;
   if (!handled && (rc = fused_strip_try(p, a, batch, C, d_scores, d_sums, s, stream, &handled))) return rc;
+  if (!handled && (rc = fused_wstrip512_try(p, a, batch, C, d_scores, d_sums, s, stream, &handled))) return rc;
   if (!handled && (rc = fused_strip512_try(p, a, batch, C, d_scores, d_sums, s, stream, &handled))) return rc;
   if (!handled && (rc = fused_fast_try(p, a, batch, C, d_scores, d_sums, s, stream, &handled))) return rc;
   if (!handled) {

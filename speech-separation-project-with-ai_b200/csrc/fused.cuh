@@ -155,6 +155,8 @@ int fused_wstrip_try(const sep_plan *p, const FusedArgs &a, int batch, int C, do
                      double *d_sums, Scratch &s, cudaStream_t stream, bool *handled);
 int fused_strip_try(const sep_plan *p, const FusedArgs &a, int batch, int C, double *d_scores,
                     double *d_sums, Scratch &s, cudaStream_t stream, bool *handled);
+int fused_wstrip512_try(const sep_plan *p, const FusedArgs &a, int batch, int C, double *d_scores,
+                        double *d_sums, Scratch &s, cudaStream_t stream, bool *handled);
 int fused_strip512_try(const sep_plan *p, const FusedArgs &a, int batch, int C, double *d_scores,
                        double *d_sums, Scratch &s, cudaStream_t stream, bool *handled);
 int fused_fast_try(const sep_plan *p, const FusedArgs &a, int batch, int C, double *d_scores,

@@ -378,10 +378,12 @@ def test_fused_strip_edges(sep, oracle, key, n_src, n, batch):
     assert int(res2["pit_perm"][0]) == int(want2["pit"]["idx"][0])
 
 
-@pytest.mark.parametrize("key,n,batch", [("blackman_256_128", 32000, 8), ("hann_256_64", 6001, 5)])
+@pytest.mark.parametrize("key,n,batch", [("blackman_256_128", 32000, 8), ("hann_256_64", 6001, 5),
+                                         ("hann_512_128", 24000, 7), ("hann_512_128", 5003, 3)])
 def test_fused_two_strip_kernels_agree(sep, oracle, monkeypatch, key, n, batch):
-    """Two sources at size 256 run the whole-warp strips (fused_wstrip.cu); SEPCORE_FORCE_HALFWARP=1 sends the
-    same call through the half-warp strips (fused_strip.cu).  Two independent kernels (different FFT
+    """Two sources at size 256 run the whole-warp strips (fused_wstrip.cu), size 512/128 the whole-warp 512-point
+    strips (fused_wstrip512.cu); SEPCORE_FORCE_HALFWARP=1 sends the same call through the half-warp strips
+    (fused_strip.cu / fused_strip512.cu).  Two independent kernels (different FFT
     factorisation, different strip partition): same estimates up to float32 round-off, identical permutations,
     scores inside the contract -- and the half-warp kernel stays covered against the oracle."""
     cfg = CONFIGS[key]
