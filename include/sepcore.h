@@ -246,6 +246,31 @@ int sep_audiowrite_i16_f32(const float *data, int batch, int64_t n, int normaliz
 int sep_audiowrite_i16_f64(const double *data, int batch, int64_t n, int normalize, int16_t *out,
                            int64_t *clipped, int mem, void *stream);
 
+/* ---- per-batch reduction without a collective on the step ("B200-native refinement") ---- */
+/* The path's only cross-utterance operation is the SUM of [loss, SI-SDR, SDR, n] over the batch (pit_loss
+ * uPIT_baseline.ipynb:1055; eval_* evaluate_metrics.py:53,90).  With one process per GPU the reference design is one
+ * all-reduce of those 32 bytes per batch -- 30-50 us of collective latency against a 21 us step.  Here the fused
+ * kernel itself, in the epilogue that adds the batch sums, stores this rank's four float64 values into EVERY rank's
+ * inbox over NVLink (peer-mapped memory, plain stores + a system-scope fence + an arrival counter): an all-gather by
+ * one-sided puts; a reader adds the `world` rows once its own synchronisation says the step is done
+ * (arrived[slot] == world).  No kernel ever waits on another rank.
+ *   inbox layout (one per rank, sep_peer_alloc): [slots][world][4] float64, then [slots] uint64 arrival counters.
+ *   sep_peer_alloc   cudaMalloc + zero fill + IPC handle (64 bytes) to send to the other ranks (any transport)
+ *   sep_peer_open    maps another rank's inbox from its handle;  sep_peer_close / sep_peer_free undo the two
+ *   sep_fused_separate_push_f32 = sep_fused_separate_ws_f32 in device mode + the push: peer_inboxes is a DEVICE array
+ *   of `world` inbox pointers (this rank's own allocation at index `rank`), `slot` the row to write. */
+int sep_peer_alloc(int64_t bytes, void **ptr, unsigned char *handle64);
+int sep_peer_open(const unsigned char *handle64, void **ptr);
+int sep_peer_close(void *ptr);
+int sep_peer_free(void *ptr);
+int sep_fused_separate_push_f32(const sep_plan *plan, const float *mix, const float *masks,
+                                const float *refs, const float *frame_lengths,
+                                const int32_t *valid_samples, int batch, int n_src,
+                                int64_t n_samples, float *est, double *scores, double *sums,
+                                void *workspace, int64_t workspace_bytes,
+                                void *const *peer_inboxes, int world, int rank, int slot, int slots,
+                                void *stream);
+
 /* ---- feature / label records ---- */
 /* The record the reference writes for every utterance: make_sequence_example(inputs, labels, length, name)
  * (parallel_stft_single.py:238-254, parallel_stft.py:217-229) serialised and framed by tf.io.TFRecordWriter

@@ -277,12 +277,51 @@ extern "C" int sep_fused_separate_f32(const sep_plan *p, const float *mix, const
                                    n_samples, est, scores, sums, nullptr, 0, mem, stream);
 }
 
+struct PushTarget {
+  double *const *peers = nullptr;
+  int world = 0, rank = 0, slot = 0, slots = 0;
+};
+
+static int fused_separate(const sep_plan *p, const float *mix, const float *masks, const float *refs,
+                          const float *frame_lengths, const int32_t *valid_samples, int batch, int n_src,
+                          int64_t n_samples, float *est, double *scores, double *sums, void *workspace,
+                          int64_t workspace_bytes, int mem, void *stream_, const PushTarget &push);
+
 extern "C" int sep_fused_separate_ws_f32(const sep_plan *p, const float *mix, const float *masks,
                                          const float *refs, const float *frame_lengths,
                                          const int32_t *valid_samples, int batch, int n_src,
                                          int64_t n_samples, float *est, double *scores,
                                          double *sums, void *workspace, int64_t workspace_bytes,
                                          int mem, void *stream_) {
+  return fused_separate(p, mix, masks, refs, frame_lengths, valid_samples, batch, n_src, n_samples, est, scores, sums,
+                        workspace, workspace_bytes, mem, stream_, PushTarget{});
+}
+
+extern "C" int sep_fused_separate_push_f32(const sep_plan *p, const float *mix, const float *masks,
+                                           const float *refs, const float *frame_lengths,
+                                           const int32_t *valid_samples, int batch, int n_src,
+                                           int64_t n_samples, float *est, double *scores, double *sums,
+                                           void *workspace, int64_t workspace_bytes,
+                                           void *const *peer_inboxes, int world, int rank, int slot, int slots,
+                                           void *stream_) {
+  SEP_REQUIRE(peer_inboxes && world >= 1 && world <= 32 && rank >= 0 && rank < world && slots >= 1 && slot >= 0 &&
+                  slot < slots,
+              "sep_fused_separate_push_f32: bad push target (world=%d rank=%d slot=%d slots=%d)", world, rank, slot, slots);
+  SEP_REQUIRE(refs && scores && sums, "sep_fused_separate_push_f32: the pushed sums need refs, scores and sums");
+  PushTarget push;
+  push.peers = reinterpret_cast<double *const *>(peer_inboxes);
+  push.world = world;
+  push.rank = rank;
+  push.slot = slot;
+  push.slots = slots;
+  return fused_separate(p, mix, masks, refs, frame_lengths, valid_samples, batch, n_src, n_samples, est, scores, sums,
+                        workspace, workspace_bytes, SEP_MEM_DEVICE, stream_, push);
+}
+
+static int fused_separate(const sep_plan *p, const float *mix, const float *masks, const float *refs,
+                          const float *frame_lengths, const int32_t *valid_samples, int batch, int n_src,
+                          int64_t n_samples, float *est, double *scores, double *sums, void *workspace,
+                          int64_t workspace_bytes, int mem, void *stream_, const PushTarget &push) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SEP_REQUIRE(p && mix && masks, "sep_fused_separate_f32: null argument");
   SEP_REQUIRE(n_src >= 1 && n_src <= SEP_MAX_SOURCES, "sep_fused_separate_f32: n_src=%d out of range",
@@ -316,6 +355,11 @@ extern "C" int sep_fused_separate_ws_f32(const sep_plan *p, const float *mix, co
   if ((rc = stage_out(s, sums, static_cast<size_t>(4), mem, &d_sums))) return rc;
   a.n = n_samples;
   a.batch = batch;
+  a.peers = push.peers;
+  a.world = push.world;
+  a.rank = push.rank;
+  a.push_slot = push.slot;
+  a.push_slots = push.slots;
   a.lookahead = 0;
   a.T = T;
   a.size = p->size;

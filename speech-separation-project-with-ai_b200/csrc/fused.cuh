@@ -17,6 +17,11 @@ struct FusedArgs {
   double *scores;         // [B, stride]   (in-kernel finalisation, fast path)
   double *sums;           // [4] or null
   int *counters;          // [B + 1] zero on entry, left zero: tiles done per utterance, utterances done
+  // per-batch reduction without a collective call (sep_fused_separate_push_f32): the CTA that adds the batch sums also
+  // PUSHES them into every rank's inbox over NVLink -- peers[p] = rank p's inbox, [slots][world][4] float64 followed by
+  // [slots] uint64 arrival counters; this rank's row of slot `push_slot`
+  double *const *peers;
+  int world, rank, push_slot, push_slots;
   int64_t n;
   int T, size, shift, pad, tb, tiles;
   int batch, lookahead;   // lookahead: tiles ahead of this CTA to pull into L2 (0 = off)
@@ -26,6 +31,22 @@ struct FusedArgs {
   const float2 *tw_half, *tw_full, *tw16;
   const float2 *win2_t, *syn2_t, *tw512_t;   // size 512 strip kernel tables, [16][18]
 };
+
+#ifdef __CUDACC__
+// Called by one whole warp that holds the batch sums on every lane.  Lane p < world stores the four float64 values into
+// rank p's inbox (peer-mapped memory: plain stores that travel over NVLink / NVSwitch), makes them visible system-wide
+// and bumps that inbox's arrival counter.  Nothing ever waits here: a reader checks arrived[slot] == world after its own
+// synchronisation (stream / host), then adds the `world` rows -- an all-gather by one-sided puts plus a local reduction.
+__device__ __forceinline__ void push_sums(const FusedArgs &a, int lane, double s0, double s1, double s2, double n) {
+  if (a.peers == nullptr || lane >= a.world) return;
+  double *inbox = a.peers[lane];
+  double *row = inbox + (static_cast<int64_t>(a.push_slot) * a.world + a.rank) * 4;
+  row[0] = s0; row[1] = s1; row[2] = s2; row[3] = n;
+  __threadfence_system();
+  unsigned long long *arrived = reinterpret_cast<unsigned long long *>(inbox + static_cast<int64_t>(a.push_slots) * a.world * 4);
+  atomicAdd_system(arrived + a.push_slot, 1ull);
+}
+#endif
 
 template <int C>
 struct FusedVals {
@@ -113,13 +134,14 @@ __device__ __forceinline__ void finalize_in_kernel(const FusedArgs &a, int b, in
     }
     s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
     if (lane == 0) { a.sums[0] = s0; a.sums[1] = s1; a.sums[2] = s2; a.sums[3] = a.batch; }
+    push_sums(a, lane, s0, s1, s2, a.batch);
   }
   if (lane == 0) a.counters[a.batch] = 0;
 }
 
 // sums[4] = {sum pit_loss, sum si_best, sum sdr_best, batch}; one warp, fixed order.
 static __global__ void fused_sums_kernel(const double *__restrict__ scores, int batch, int stride,
-                                  int off_pit, int off_si, int off_sdr, double *__restrict__ sums) {
+                                  int off_pit, int off_si, int off_sdr, double *__restrict__ sums, const FusedArgs a) {
   const int lane = threadIdx.x;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0;
   for (int b = lane; b < batch; b += 32) {
@@ -130,6 +152,7 @@ static __global__ void fused_sums_kernel(const double *__restrict__ scores, int 
   }
   s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
   if (lane == 0) { sums[0] = s0; sums[1] = s1; sums[2] = s2; sums[3] = batch; }
+  push_sums(a, lane, s0, s1, s2, batch);
 }
 
 template <int C>
@@ -143,7 +166,7 @@ static int launch_fused_finalize(const FusedArgs &a, int batch, double *d_scores
     const int P = factorial(C);
     const int off_pit = C * C + P + 1, off_si = C * C + P + 2 + C * C;
     const int off_sdr = off_si + 2 + C * C;
-    fused_sums_kernel<<<1, 32, 0, stream>>>(d_scores, batch, stride, off_pit, off_si, off_sdr, d_sums);
+    fused_sums_kernel<<<1, 32, 0, stream>>>(d_scores, batch, stride, off_pit, off_si, off_sdr, d_sums, a);
     SEP_LAUNCHED();
   }
   return SEP_OK;

@@ -72,6 +72,36 @@ const char *sep_last_kernel(void) { return t_kernel; }
 
 int64_t sep_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+// ---- peer-visible device memory for the one-sided per-batch reduction (sep_fused_separate_push_f32) ----
+int sep_peer_alloc(int64_t bytes, void **ptr, unsigned char *handle64) {
+  SEP_REQUIRE(ptr && handle64 && bytes > 0, "sep_peer_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  SEP_CUDA(cudaMalloc(ptr, static_cast<size_t>(bytes)));          // a dedicated allocation: IPC handles name whole allocations
+  SEP_CUDA(cudaMemset(*ptr, 0, static_cast<size_t>(bytes)));
+  cudaIpcMemHandle_t h;
+  SEP_CUDA(cudaIpcGetMemHandle(&h, *ptr));
+  memcpy(handle64, &h, 64);
+  return SEP_OK;
+}
+
+int sep_peer_open(const unsigned char *handle64, void **ptr) {
+  SEP_REQUIRE(ptr && handle64, "sep_peer_open: bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  SEP_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));   // maps the peer's memory (NVLink P2P)
+  return SEP_OK;
+}
+
+int sep_peer_close(void *ptr) {
+  if (ptr) SEP_CUDA(cudaIpcCloseMemHandle(ptr));
+  return SEP_OK;
+}
+
+int sep_peer_free(void *ptr) {
+  if (ptr) SEP_CUDA(cudaFree(ptr));
+  return SEP_OK;
+}
+
 int sep_profile_enable(int on) {
   std::lock_guard<std::mutex> lock(g_prof_mutex);
   g_prof_on = on != 0;

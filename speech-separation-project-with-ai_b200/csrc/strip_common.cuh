@@ -72,6 +72,7 @@ __device__ __forceinline__ void finalize_by_warp(const FusedArgs &a, int b, int 
     }
     s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
     if (lane == 0) { a.sums[0] = s0; a.sums[1] = s1; a.sums[2] = s2; a.sums[3] = a.batch; }
+    push_sums(a, lane, s0, s1, s2, a.batch);
   }
   if (lane == 0) a.counters[a.batch] = 0;
 }

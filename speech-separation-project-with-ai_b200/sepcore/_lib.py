@@ -62,6 +62,12 @@ PROTOTYPES = {
     "sep_fused_workspace_bytes": (_int, [_vp, _int, _int, _i64, C.POINTER(_i64)]),
     "sep_fused_separate_ws_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _i64, _vp, _vp,
                                          _vp, _vp, _i64, _int, _vp]),
+    "sep_fused_separate_push_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _i64, _vp, _vp,
+                                           _vp, _vp, _i64, _vp, _int, _int, _int, _int, _vp]),
+    "sep_peer_alloc": (_int, [_i64, C.POINTER(_vp), C.c_char_p]),
+    "sep_peer_open": (_int, [C.c_char_p, C.POINTER(_vp)]),
+    "sep_peer_close": (_int, [_vp]),
+    "sep_peer_free": (_int, [_vp]),
     "sep_pit_mse_f32": (_int, [_vp, _vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "sep_score_batch_f32": (_int, [_vp, _vp, _i64p, _i64p, _i64p, _int, _int, _i64, _i64, _vp, _vp,
                                    _int, _vp]),

@@ -55,7 +55,7 @@ def workspace_bytes(batch, n_src, n_samples, size=256, shift=128, window=None):
 
 
 def separate_and_score(mix, masks, refs=None, frame_lengths=None, valid_samples=None,
-                       size=256, shift=128, window=None, want_est=True, out=None, workspace=None):
+                       size=256, shift=128, window=None, want_est=True, out=None, workspace=None, push=None):
     """One fused pass.
 
     mix [B, N] float32; masks [B, C, T, F] float32 with T = frames(N), F = size/2+1;
@@ -71,6 +71,8 @@ def separate_and_score(mix, masks, refs=None, frame_lengths=None, valid_samples=
     bytes (`torch.zeros`; the library leaves it zero-filled, so one buffer can be
     reused by successive calls on one stream); with it the call allocates nothing, so
     it can be captured into a CUDA graph.
+    `push` (device mode, refs given): `sepcore.distributed.PeerSums.target(slot)` -- the kernel also stores this
+    call's batch sums into every rank's inbox over NVLink (per-batch reduction without a collective call).
     """
     plan = get_plan(size, shift, window, True)
     lib = _lib.load()
@@ -135,11 +137,21 @@ def separate_and_score(mix, masks, refs=None, frame_lengths=None, valid_samples=
     ws_ptr, ws_bytes = None, 0
     if workspace is not None and dev:
         ws_ptr, ws_bytes = ptr(workspace), int(workspace.numel() * workspace.element_size())
-    _lib.check(lib.sep_fused_separate_ws_f32(plan.handle, ptr(m), ptr(k), ptr(r), ptr(fl), ptr(vs),
-                                             batch, n_src, n, ptr(est), ptr(scores), ptr(sums),
-                                             ws_ptr, ws_bytes, mem,
-                                             current_stream(mem, m if dev else None)),
-               "sep_fused_separate_ws_f32")
+    if push is not None:
+        if not dev or r is None:
+            raise ValueError("push needs CUDA tensors and refs")
+        peers, world, rank, slot, slots = push
+        _lib.check(lib.sep_fused_separate_push_f32(plan.handle, ptr(m), ptr(k), ptr(r), ptr(fl), ptr(vs),
+                                                   batch, n_src, n, ptr(est), ptr(scores), ptr(sums),
+                                                   ws_ptr, ws_bytes, ptr(peers), int(world), int(rank), int(slot),
+                                                   int(slots), current_stream(mem, m)),
+                   "sep_fused_separate_push_f32")
+    else:
+        _lib.check(lib.sep_fused_separate_ws_f32(plan.handle, ptr(m), ptr(k), ptr(r), ptr(fl), ptr(vs),
+                                                 batch, n_src, n, ptr(est), ptr(scores), ptr(sums),
+                                                 ws_ptr, ws_bytes, mem,
+                                                 current_stream(mem, m if dev else None)),
+                   "sep_fused_separate_ws_f32")
     res = {}
     if want_est:
         res["est"] = est

@@ -31,15 +31,18 @@ class GraphedSeparator:
     captured into the graph on ONE dedicated communication stream, in step order -- the same
     total order on every rank, as NCCL requires -- waiting only on the step that produced the
     row, so the compute lanes never wait for the collective (per-batch all-reduce).
+    push: None, or a `sepcore.distributed.PeerSums` with >= `steps` slots: step s also pushes its sums into slot
+    s of every rank's inbox from inside the fused kernel (no collective call at all).
     """
 
     def __init__(self, buffer_sets, steps, size=256, shift=128, window=None, want_est=True, streams=1,
-                 reduce_each_step=None):
+                 reduce_each_step=None, push=None):
         import torch
 
         self.sets = buffer_sets
         self.steps = int(steps)
         self.kw = dict(size=size, shift=shift, window=window, want_est=want_est)
+        self.push = push
         first = buffer_sets[0]
         batch, n = (int(v) for v in first["mix"].shape)
         n_src = int(first["masks"].shape[1])
@@ -98,7 +101,7 @@ class GraphedSeparator:
             o["sums"] = self.sums[s]
         return fused.separate_and_score(
             b["mix"], b["masks"], b.get("refs"), b.get("frame_lengths"), b.get("valid_samples"),
-            out=o, workspace=o["workspace"], **self.kw)
+            out=o, workspace=o["workspace"], push=None if self.push is None else self.push.target(s), **self.kw)
 
     def replay(self):
         self.graph.replay()

@@ -22,8 +22,9 @@ ap.add_argument("--size", type=int, default=256)
 ap.add_argument("--shift", type=int, default=128)
 ap.add_argument("--window", default="blackman")
 args = ap.parse_args()
-sets = [{k: torch.from_numpy(v).cuda() for k, v in bench.make_set(args, seed=i).items()} for i in range(3)]
-kw = dict(size=args.size, shift=args.shift, window=bench.window_fn(args.window))
+wl = bench.Workload("run_steps", args.batch, args.seconds, args.sources, args.size, args.shift, args.window)
+sets = [{k: torch.from_numpy(v).cuda() for k, v in wl.make_set(seed=i).items()} for i in range(3)]
+kw = wl.kw()
 for s in range(args.steps):
     d = sets[s % 3]
     res = sepcore.separate_and_score(d["mix"], d["masks"], d["refs"], **kw)
