@@ -392,8 +392,8 @@ def measure_fused(ctx, wl, steps, warmup, streams, reduce_mode="bucket", alone_l
         dev_sets = [{k: torch.from_numpy(v).to(ctx.dev) for k, v in wl.make_set(1000 * ctx.rank + i).items()}
                     for i in range(wl.n_sets)]
     torch.cuda.synchronize()
-    per_batch = reduce_mode == "per_batch" and ctx.world > 1
-    red = sepcore.distributed.all_reduce_sums if per_batch else None
+    per_batch = reduce_mode in ("per_batch", "push") and ctx.world > 1
+    red = sepcore.distributed.all_reduce_sums if per_batch and reduce_mode == "per_batch" else None
     warm = sepcore.GraphedSeparator(dev_sets, max(warmup, 3), streams=streams, **kw)
     warm.replay()
     if ctx.world > 1:
@@ -414,10 +414,15 @@ def measure_fused(ctx, wl, steps, warmup, streams, reduce_mode="bucket", alone_l
     total_steps = reps * steps
     block = min(total_steps, 1024)
     n_blocks, tail = divmod(total_steps, block)
-    graph = sepcore.GraphedSeparator(dev_sets, block, streams=streams, reduce_each_step=red, **kw)
-    tail_graph = sepcore.GraphedSeparator(dev_sets, tail, streams=streams, reduce_each_step=red, **kw) if tail else None
+    peer = sepcore.distributed.PeerSums(slots=block) if per_batch and reduce_mode == "push" else None
+    graph = sepcore.GraphedSeparator(dev_sets, block, streams=streams, reduce_each_step=red, push=peer, **kw)
+    tail_graph = sepcore.GraphedSeparator(dev_sets, tail, streams=streams, reduce_each_step=red, push=peer, **kw) if tail else None
     graph.replay()
     torch.cuda.synchronize()
+    if peer is not None:
+        ctx.barrier()
+        peer.arrived.zero_()
+        ctx.barrier()
     sampler = ClockSampler(ctx.local)
     sampler.start()
     ctx.barrier()
@@ -439,6 +444,16 @@ def measure_fused(ctx, wl, steps, warmup, streams, reduce_mode="bucket", alone_l
     ms_total = ctx.max_over_ranks(ms_total)
     ms_step = ms_total / total_steps
     sums = graph.sums[0].cpu().numpy().tolist()
+    push_check = None
+    if peer is not None:
+        # after the barrier every rank's pushes have landed: the inbox rows must add up to the NCCL all-reduce
+        want = graph.sums.clone()
+        dist.all_reduce(want)
+        got = peer.reduced()[:block]
+        push_check = {"arrived_min": int(peer.arrived[:block].min().item()), "arrived_expected": ctx.world * n_blocks,
+                      "max_rel_diff_vs_nccl": float(((got - want).abs() / want.abs().clamp_min(1e-300)).max().item())}
+        ctx.barrier()
+        peer.close()
 
     # the dominant kernel alone: eager launches, one at a time, bracketed by events in the library
     n = wl.n
@@ -481,7 +496,7 @@ def measure_fused(ctx, wl, steps, warmup, streams, reduce_mode="bucket", alone_l
     }
     return {"ms_total": ms_total, "replays": reps, "ms_per_step": ms_step, "clocks": clocks, "sums": sums,
             "launches_per_step": launches_per_step, "roofline": roofline, "graph_steps": block,
-            "graph_replays": n_blocks + (1 if tail else 0),
+            "graph_replays": n_blocks + (1 if tail else 0), "push_check": push_check,
             "n_streams": graph.n_streams, "dev_sets": dev_sets,
             "value": ctx.world * wl.batch * wl.seconds / (ms_step * 1e-3)}
 
@@ -795,6 +810,17 @@ def run_sepcore(args):
                            "timing": {"replays": pb["replays"], "graph_steps": pb["graph_steps"], "timed_ms": pb["ms_total"]},
                            "roofline": pb["roofline"], "clocks": pb["clocks"],
                            "vs_bucketed": pb["ms_per_step"] / r["ms_per_step"]})
+            # ... and with no collective call at all: the kernel's epilogue pushes the sums into every rank's inbox
+            ps = measure_fused(ctx, wl, args.steps, 3, args.streams, reduce_mode="push", alone_launches=8,
+                               dev_sets=r["dev_sets"])
+            extras.append({"name": "cfg2_per_batch_push", "metric": METRIC, "value": ps["value"], "unit": UNIT,
+                           "n_gpus": ctx.world, "ms_per_step": ps["ms_per_step"], "scaling": "weak", "dtype": "f32",
+                           "config": dict(wl.config(), reduction="PER STEP, no collective call: the fused kernel stores its "
+                                          "[loss, SI-SDR, SDR, n] row into every rank's inbox over NVLink (peer-mapped "
+                                          "memory, sep_fused_separate_push_f32); readers add the rows"),
+                           "timing": {"replays": ps["replays"], "graph_steps": ps["graph_steps"], "timed_ms": ps["ms_total"]},
+                           "roofline": ps["roofline"], "clocks": ps["clocks"], "check": ps["push_check"],
+                           "vs_bucketed": ps["ms_per_step"] / r["ms_per_step"]})
     e2e = None
     if not args.no_e2e:
         e2e = measure_e2e(ctx, wl, args.steps)

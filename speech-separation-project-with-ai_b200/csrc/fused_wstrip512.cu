@@ -11,8 +11,9 @@
 // Lane q owns the bin pairs (kA, kB) = (q + 32 r, 256 - q - 32 r), r = 0..3 -- its own Z[kA] and ONE shuffled partner
 // Z[256 - kA] (lane (32 - q) % 32, register 7 - r) give both bins, so a transform needs 8 shuffles, not 16 -- and lane 0
 // additionally bin 128 (slot 4).  Spectra are kept PLANAR per pair, (Re X[kA], Re X[kB]) / (Im ...), so |X|, the PSA
-// labels, the squared differences and the mask multiply run as packed FP32 on both bins at once, exactly as the
-// 256-point kernel (fused_wstrip.cu) does on its frame pairs; mask rows (257 floats, 4-byte aligned) are read straight
+// labels and the squared differences run as packed FP32 on both bins at once, exactly as the 256-point kernel
+// (fused_wstrip.cu) does on its frame pairs (the mixture also keeps the complex form X[kA], conj X[kB], which is what
+// the inverse butterflies want: every butterfly is six packed instructions, no scalar arithmetic); mask rows (257 floats, 4-byte aligned) are read straight
 // into registers as two lane-contiguous 128-byte runs per source (ascending kA, descending kB): no shared-memory
 // staging and none of the 4-byte cp.async traffic of the half-warp kernel (fused_strip512.cu).
 //
@@ -52,9 +53,11 @@ struct WStrip512Geom {
 };
 
 // Forward real-transform butterfly of slot r: this lane's Z[kA] (register r) and the partner Z[256 - kA].
-// U = i W512^kA.  XR = (Re X[kA], Re X[kB]), XI = (Im X[kA], Im X[kB]), kB = 256 - kA.
-__device__ __forceinline__ void w5_split(const float2 (&v)[8], int q, int r, float2 U, float2 &XR, float2 &XI) {
-  float2 P = v[4];                                 // slot 4: bin 128 is its own partner (lane 0 only)
+// U = i W512^kA.  Everything is packed FP32 with operand swizzles / per-half negation (free on sm_100):
+//   E = A + conj P, F = A - conj P, T = U F  ->  planar  XR = (Re X[kA], Re X[kB]) = (E.x - T.x, E.x + T.x),
+//   XI = (Im X[kA], Im X[kB]) = (E.y - T.y, -E.y - T.y);  complex  XA = X[kA] = E - T,  XBc = conj X[kB] = E + T.
+__device__ __forceinline__ void w5_partner(const float2 (&v)[8], int q, int r, float2 &A, float2 &P) {
+  P = v[4];                                        // slot 4: bin 128 is its own partner (lane 0 only)
   if (r < 4) {
     const int src = (32 - q) & 31;
     float2 got;
@@ -63,20 +66,41 @@ __device__ __forceinline__ void w5_split(const float2 (&v)[8], int q, int r, flo
     const float2 own = v[(8 - r) & 7];
     P = (q == 0) ? own : got;
   }
-  const float2 A = v[r < 4 ? r : 4];
-  const float2 S = __fadd2_rn(A, P);                                 // E = (S.x, D.y)
-  const float2 D = __fadd2_rn(A, make_float2(-P.x, -P.y));           // F = (D.x, S.y)
-  const float tx = fmaf(U.x, D.x, -U.y * S.y), ty = fmaf(U.x, S.y, U.y * D.x);   // T = U F
-  XR = make_float2(S.x - tx, S.x + tx);
-  XI = make_float2(D.y - ty, -D.y - ty);
+  A = v[r < 4 ? r : 4];
+}
+__device__ __forceinline__ void w5_split(const float2 (&v)[8], int q, int r, float2 U, float2 &XR, float2 &XI) {
+  float2 A, P;
+  w5_partner(v, q, r, A, P);
+  const float2 E = __fadd2_rn(A, make_float2(P.x, -P.y));
+  const float2 F = __fadd2_rn(A, make_float2(-P.x, P.y));
+  const float2 Tt = cmul(F, U);
+  XR = __fadd2_rn(make_float2(E.x, E.x), make_float2(-Tt.x, Tt.x));
+  XI = __fadd2_rn(make_float2(E.y, -E.y), make_float2(-Tt.y, -Tt.y));
+}
+// the mixture also keeps the complex form for the inverse butterflies
+__device__ __forceinline__ void w5_split_both(const float2 (&v)[8], int q, int r, float2 U, float2 &XR, float2 &XI,
+                                              float2 &XA, float2 &XBc) {
+  float2 A, P;
+  w5_partner(v, q, r, A, P);
+  const float2 E = __fadd2_rn(A, make_float2(P.x, -P.y));
+  const float2 F = __fadd2_rn(A, make_float2(-P.x, P.y));
+  const float2 Tt = cmul(F, U);
+  XR = __fadd2_rn(make_float2(E.x, E.x), make_float2(-Tt.x, Tt.x));
+  XI = __fadd2_rn(make_float2(E.y, -E.y), make_float2(-Tt.y, -Tt.y));
+  XA = __fadd2_rn(E, make_float2(-Tt.x, -Tt.y));
+  XBc = __fadd2_rn(E, Tt);
 }
 
-// Inverse butterfly of slot r: masked planar spectrum (YR, YI) -> Z'[kA] and the value for the mirror index.
-__device__ __forceinline__ void w5_unsplit(float2 YR, float2 YI, float2 U, float2 &ZA, float2 &ZB) {
-  const float ex = YR.x + YR.y, ey = YI.x - YI.y, fx = YR.x - YR.y, fy = YI.x + YI.y;
-  const float ux = -fmaf(U.x, fx, U.y * fy), uy = fmaf(U.y, fx, -U.x * fy);          // i conj(W) Fy = (-U.x, U.y) Fy
-  ZA = make_float2(ex + ux, ey + uy);
-  ZB = make_float2(ex - ux, uy - ey);
+// Inverse butterfly of slot r: Y[kA] = mA X[kA], conj Y[kB] = mB conj X[kB];  Ey = Y[kA] + conj Y[kB],
+// Fy = Y[kA] - conj Y[kB], V = i conj(W) Fy = (-U.x, U.y) Fy;  Z'[kA] = Ey + V,  Z'[kB] = conj(Ey - V).
+__device__ __forceinline__ void w5_unsplit(float2 XA, float2 XBc, float2 mk, float2 U, float2 &ZA, float2 &ZB) {
+  const float2 YA = __fmul2_rn(XA, make_float2(mk.x, mk.x));
+  const float2 YB = __fmul2_rn(XBc, make_float2(mk.y, mk.y));
+  const float2 Ey = __fadd2_rn(YA, YB);
+  const float2 Fy = __fadd2_rn(YA, make_float2(-YB.x, -YB.y));
+  const float2 V = cmul(Fy, make_float2(-U.x, U.y));
+  ZA = __fadd2_rn(Ey, V);
+  ZB = __fadd2_rn(make_float2(Ey.x, -Ey.y), make_float2(-V.x, V.y));
 }
 
 template <int C, bool SCORE, int W, int CPS>
@@ -169,15 +193,18 @@ __global__ void __launch_bounds__(W * 32, CPS) wstrip512_kernel(const FusedArgs 
 
     float2 mab[C][5];                                               // (mask at kA, mask at kB) per slot
     auto load_masks = [&](int ta) {
-      // rows beyond T - 1 multiply all-zero spectra: any valid row will do (no predicates)
-      const float *row = mask_b + min(ta, T - 1) * BINS;
+      // rows beyond T - 1 multiply all-zero spectra: any valid row will do (no predicates).  Two lane bases per
+      // row (ascending kA run, descending kB run) and compile-time offsets: no per-load address arithmetic.
+      const float *pa = mask_b + min(ta, T - 1) * BINS + lane;
+      const float *pb = pa + (256 - 2 * lane);
 #pragma unroll
       for (int i = 0; i < C; ++i) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) mab[i][r] = make_float2(__ldg(row + lane + 32 * r), __ldg(row + 256 - lane - 32 * r));
-        const float m128 = __ldg(row + 128);
+        for (int r = 0; r < 4; ++r) mab[i][r] = make_float2(__ldg(pa + 32 * r), __ldg(pb - 32 * r));
+        const float m128 = __ldg(pa - lane + 128);
         mab[i][4] = make_float2(m128, m128);
-        row += mask_q;
+        pa += mask_q;
+        pb += mask_q;
       }
     };
 
@@ -230,7 +257,8 @@ __global__ void __launch_bounds__(W * 32, CPS) wstrip512_kernel(const FusedArgs 
       };
 
       float2 v[8];
-      float2 XR[5], XI[5];                                          // mixture spectra, planar over (kA, kB)
+      float2 XR[5], XI[5];                                          // mixture spectra, planar over (kA, kB) (labels)
+      float2 XA[5], XBc[5];                                         // ... and complex: X[kA], conj X[kB] (inverse butterflies)
       float2 inv[5], mag[5];                                        // 1/|X|, gated |X|
       float pmin = 1.f;
       const float own_w = (ta >= own_frame0 && ta < T) ? 1.f : 0.f;
@@ -271,7 +299,17 @@ __global__ void __launch_bounds__(W * 32, CPS) wstrip512_kernel(const FusedArgs 
       };
       auto mixture_spectra = [&]() {
 #pragma unroll
-        for (int r = 0; r < 5; ++r) w5_split(v, lane, r, up[r], XR[r], XI[r]);
+        for (int r = 0; r < 5; ++r) {
+          if (SCORE) w5_split_both(v, lane, r, up[r], XR[r], XI[r], XA[r], XBc[r]);
+          else {
+            float2 A, P;
+            w5_partner(v, lane, r, A, P);
+            const float2 E = __fadd2_rn(A, make_float2(P.x, -P.y));
+            const float2 Tt = cmul(__fadd2_rn(A, make_float2(-P.x, P.y)), up[r]);
+            XA[r] = __fadd2_rn(E, make_float2(-Tt.x, -Tt.y));
+            XBc[r] = __fadd2_rn(E, Tt);
+          }
+        }
         if (SCORE) {
 #pragma unroll
           for (int r = 0; r < 5; ++r) {
@@ -320,9 +358,8 @@ __global__ void __launch_bounds__(W * 32, CPS) wstrip512_kernel(const FusedArgs 
         float2 ZB[4], Z4 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int r = 0; r < 5; ++r) {
-          const float2 mk = mab[qi][r];
           float2 za, zb;
-          w5_unsplit(__fmul2_rn(XR[r], mk), __fmul2_rn(XI[r], mk), up[r], za, zb);
+          w5_unsplit(XA[r], XBc[r], mab[qi][r], up[r], za, zb);
           if (r < 4) { vv[r] = za; ZB[r] = zb; } else Z4 = za;
         }
         const int src = (32 - lane) & 31;
@@ -335,7 +372,8 @@ __global__ void __launch_bounds__(W * 32, CPS) wstrip512_kernel(const FusedArgs 
           vv[j] = (lane == 0) ? own : got;
         }
       };
-      // time frame of estimate qi -> overlap-add -> hop block ta -> HBM, Gram statistics
+      // time frame of estimate qi -> overlap-add -> hop block ta -> HBM; the finished block is kept for the Gram pass
+      float2 yo[C][2];
       auto finish = [&](const float2 (&vv)[8], auto qc) {
         constexpr int qi = decltype(qc)::value;
         float2 y[8];
@@ -347,60 +385,54 @@ __global__ void __launch_bounds__(W * 32, CPS) wstrip512_kernel(const FusedArgs 
         }
 #pragma unroll
         for (int k = 0; k < 6; ++k) carry[qi][k] = y[k + 2];
+        yo[qi][0] = y[0];
+        yo[qi][1] = y[1];
         float *out = a.est ? a.est + (static_cast<int64_t>(b) * C + qi) * a.n + gb + 2 * lane : nullptr;
-        double gq[C], eq = 0.0, rq[C];
-#pragma unroll
-        for (int j = 0; j < C; ++j) { gq[j] = 0.0; rq[j] = 0.0; }
-        const float *rf = stage + RING * SHIFT + so[0];             // reference 0 at hop block ta, this lane's pair
+        if (out == nullptr || !owned) return;
         if (plain) {
-          if (out) {
 #pragma unroll
-            for (int m = 0; m < 2; ++m) *reinterpret_cast<float2 *>(out + 64 * m) = y[m];
-          }
-          if (SCORE) {
-#pragma unroll
-            for (int m = 0; m < 2; ++m) {
-              const double e0 = static_cast<double>(y[m].x), e1 = static_cast<double>(y[m].y);
-              eq = fma(e0, e0, eq);
-              eq = fma(e1, e1, eq);
-#pragma unroll
-              for (int j = 0; j < C; ++j) {
-                const float2 r2 = *reinterpret_cast<const float2 *>(rf + j * RING * SHIFT + 64 * m);
-                const double r0 = static_cast<double>(r2.x), r1 = static_cast<double>(r2.y);
-                gq[j] = fma(e0, r0, gq[j]);
-                gq[j] = fma(e1, r1, gq[j]);
-                if (qi == 0) { rq[j] = fma(r0, r0, rq[j]); rq[j] = fma(r1, r1, rq[j]); }
-              }
-            }
-          }
-        } else if (owned) {
+          for (int m = 0; m < 2; ++m) *reinterpret_cast<float2 *>(out + 64 * m) = y[m];
+        } else {
 #pragma unroll
           for (int m = 0; m < 2; ++m) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int g = gb + 2 * lane + 64 * m + h;
-              const float ev = h == 0 ? y[m].x : y[m].y;
-              if (out && g >= 0 && g < n32) out[64 * m + h] = ev;
-              if (SCORE && g >= 0 && g < n_valid) {
-                const double e = static_cast<double>(ev);
-                eq = fma(e, e, eq);
-#pragma unroll
-                for (int j = 0; j < C; ++j) {
-                  const double r = static_cast<double>(rf[j * RING * SHIFT + 64 * m + h]);
-                  gq[j] = fma(e, r, gq[j]);
-                  if (qi == 0) rq[j] = fma(r, r, rq[j]);
-                }
-              }
-            }
+            const int g = gb + 2 * lane + 64 * m;
+            if (g >= 0 && g < n32) out[64 * m] = y[m].x;
+            if (g + 1 >= 0 && g + 1 < n32) out[64 * m + 1] = y[m].y;
           }
         }
-        if (SCORE) {
-          acc[32 * (C * C + qi)] += eq;
+      };
+      // Gram statistics <e_i, r_j>, |e_i|^2, |r_j|^2 of hop block ta for ALL estimates at once: every reference sample
+      // is read and converted once (float64: products of float32 are exact)
+      auto gram_all = [&]() {
+        if (!SCORE || !owned) return;
+        const float *rf = stage + RING * SHIFT + so[0];             // reference 0 at hop block ta, this lane's pairs
+        double e[C][4], r[C][4];
 #pragma unroll
-          for (int j = 0; j < C; ++j) acc[32 * (qi * C + j)] += gq[j];
-          if (qi == 0) {
+        for (int m = 0; m < 2; ++m) {
+          const int g = gb + 2 * lane + 64 * m;
+          const bool ok0 = plain || (g >= 0 && g < n_valid), ok1 = plain || (g + 1 >= 0 && g + 1 < n_valid);
 #pragma unroll
-            for (int j = 0; j < C; ++j) acc[32 * (C * C + C + j)] += rq[j];
+          for (int j = 0; j < C; ++j) {
+            const float2 r2 = *reinterpret_cast<const float2 *>(rf + j * RING * SHIFT + 64 * m);
+            r[j][2 * m] = ok0 ? static_cast<double>(r2.x) : 0.0;
+            r[j][2 * m + 1] = ok1 ? static_cast<double>(r2.y) : 0.0;
+            e[j][2 * m] = ok0 ? static_cast<double>(yo[j][m].x) : 0.0;
+            e[j][2 * m + 1] = ok1 ? static_cast<double>(yo[j][m].y) : 0.0;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+          double ee = 0.0, rr = 0.0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { ee = fma(e[i][k], e[i][k], ee); rr = fma(r[i][k], r[i][k], rr); }
+          acc[32 * (C * C + i)] += ee;
+          acc[32 * (C * C + C + i)] += rr;
+#pragma unroll
+          for (int j = 0; j < C; ++j) {
+            double gq = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) gq = fma(e[i][k], r[j][k], gq);
+            acc[32 * (i * C + j)] += gq;
           }
         }
       };
@@ -412,6 +444,7 @@ __global__ void __launch_bounds__(W * 32, CPS) wstrip512_kernel(const FusedArgs 
         if (it + 1 < n_it) load_masks(ta + 1);
         wfft256<true>(v, t1, t2, ex, lane);
         finish(v, Q0{});
+        gram_all();
       } else {
         float2 vb[8];
         merged(v, Q0{});
@@ -421,6 +454,7 @@ __global__ void __launch_bounds__(W * 32, CPS) wstrip512_kernel(const FusedArgs 
           wfft256x2<true>(v, vb, t1, t2, ex, lane);
           finish(v, Q0{});
           finish(vb, Q1{});
+          gram_all();
         } else {
           wfft256x2<true>(v, vb, t1, t2, ex, lane);
           finish(v, Q0{});
@@ -429,6 +463,7 @@ __global__ void __launch_bounds__(W * 32, CPS) wstrip512_kernel(const FusedArgs 
           if (it + 1 < n_it) load_masks(ta + 1);
           wfft256<true>(v, t1, t2, ex, lane);
           finish(v, Q2{});
+          gram_all();
         }
       }
       slot0 = slot0 + 1 == RING ? 0 : slot0 + 1;

@@ -46,9 +46,24 @@ def main():
         per = {k: res[k].contiguous().clone() for k in per}
     d.all_reduce_sums(sums)
     gathered = {k: d.gather_per_utterance(v, counts) for k, v in per.items()}
+    # the same reduction WITHOUT a collective call: the fused kernel pushes its sums into every rank's inbox
+    peer = d.PeerSums(slots=4)
+    if hi > lo:
+        sepcore.separate_and_score(torch.from_numpy(mix[lo:hi]).to(dev), torch.from_numpy(masks[lo:hi]).to(dev),
+                                   torch.from_numpy(refs[lo:hi]).to(dev), size=256, shift=128, push=peer.target(2))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()                       # every rank's kernel (and its pushes) has completed
+    pushed = peer.reduced()[2].cpu().numpy()
+    arrived = int(peer.arrived[2].item())
+    untouched = float(peer.rows[[0, 1, 3]].abs().sum().item())
+    if world > 1:
+        dist.barrier()
+    peer.close()
     torch.cuda.synchronize()
     if rank == 0:
-        np.savez(out_path, sums=sums.cpu().numpy(), **{k: v.cpu().numpy() for k, v in gathered.items()})
+        np.savez(out_path, sums=sums.cpu().numpy(), push_sums=pushed, push_arrived=arrived, push_untouched=untouched,
+                 **{k: v.cpu().numpy() for k, v in gathered.items()})
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -49,6 +49,11 @@ def test_sharded_results_identical_to_one_rank(world, tmp_path):
         assert abs(many["sums"][i] - many[key].sum()) <= 1e-12 * abs(many[key].sum())
         assert abs(many["sums"][i] - one["sums"][i]) <= 1e-5 * abs(one["sums"][i])
     assert many["sums"][3] == one["sums"][3] == 22
+    # the one-sided push (sep_fused_separate_push_f32) delivers the same sums as the NCCL all-reduce
+    ranks_with_work = min(world, 22)
+    assert int(many["push_arrived"]) == ranks_with_work and int(one["push_arrived"]) == 1
+    assert np.allclose(many["push_sums"], many["sums"], rtol=1e-12, atol=0) and many["push_untouched"] == 0.0
+    assert np.array_equal(one["push_sums"], one["sums"])
 
 
 def test_scoring_sharded_bit_identical(tmp_path):
