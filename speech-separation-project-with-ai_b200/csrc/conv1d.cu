@@ -12,6 +12,8 @@
 // 64 x 64 output tile per CTA, 4 x 4 register micro-tile per thread, K staged
 // through shared memory 16 at a time.  (The tcgen05 variant for the BASELINE
 // N=256/L=16 shape is tracked in DESIGN.md.)
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace sep {
@@ -87,6 +89,103 @@ conv1d_kernel(const float *__restrict__ x, const float *__restrict__ w, const fl
   }
 }
 
+// ---- weights-resident variant for small contractions (the reference shape: K = taps * c_in = 80, 129 filters) ----
+// The whole kernel matrix W [K, filters] (41 KB) stays in shared memory for the lifetime of a persistent CTA; a tile is
+// 128 output rows, whose im2col rows are ONE contiguous span of x ((128 - 1) * stride * c_in + K floats), staged with
+// 16-byte loads.  256 threads = 16 row groups x 16 column groups; a thread owns 8 rows x NT columns (columns
+// tx + 16 c: conflict-free weight reads, broadcast activation reads), i.e. 8 NT FFMAs per 8 + NT shared loads -- FMA-bound,
+// and no column tile is ever 1/64 full (the 64 x 64 kernel spends a third of its CTAs on filter 128 alone).
+// Exact fp32, same summation order per output as the generic kernel (k ascending).
+template <int NT>
+__global__ void __launch_bounds__(256)
+conv1d_rows_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
+                   int batch, int rows, int c_in, int taps, int filters, int stride, int left, int rows_out,
+                   int act, float *__restrict__ out) {
+  extern __shared__ __align__(16) float smem_f[];
+  constexpr int RT = 128;                                   // rows per tile
+  const int K = taps * c_in, NP = 16 * NT, hop = stride * c_in;
+  const int span = (RT - 1) * hop + K;
+  float *Ws = smem_f;                                       // [K][NP], zero beyond `filters`
+  float *xs = smem_f + K * NP;                              // [span] (+ pad)
+  for (int e = threadIdx.x; e < K * NP; e += 256) {
+    const int k = e / NP, n = e - k * NP;
+    Ws[e] = n < filters ? __ldg(w + static_cast<int64_t>(k) * filters + n) : 0.f;
+  }
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float bv[NT];
+#pragma unroll
+  for (int c = 0; c < NT; ++c) bv[c] = (bias && tx + 16 * c < filters) ? __ldg(bias + tx + 16 * c) : 0.f;
+  const int tiles_per = (rows_out + RT - 1) / RT, tiles = batch * tiles_per;
+  for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const int b = t / tiles_per, r0 = (t - b * tiles_per) * RT;
+    const float *xb = x + static_cast<int64_t>(b) * rows * c_in;
+    const int64_t g0 = static_cast<int64_t>(r0 * stride - left) * c_in;      // first x element of the span
+    const int64_t n_x = static_cast<int64_t>(rows) * c_in;
+    __syncthreads();                                        // the previous tile's reads are done (and Ws is complete)
+    if (g0 >= 0 && g0 + span <= n_x && (reinterpret_cast<uintptr_t>(xb + g0) & 15) == 0) {
+      for (int e = threadIdx.x; e < span / 4; e += 256)
+        reinterpret_cast<float4 *>(xs)[e] = __ldg(reinterpret_cast<const float4 *>(xb + g0) + e);
+      for (int e = (span / 4) * 4 + threadIdx.x; e < span; e += 256) xs[e] = __ldg(xb + g0 + e);
+    } else {
+      for (int e = threadIdx.x; e < span; e += 256) {
+        const int64_t g = g0 + e;
+        xs[e] = (g >= 0 && g < n_x) ? __ldg(xb + g) : 0.f;  // zero padding on both sides ('same') / beyond the last row
+      }
+    }
+    __syncthreads();
+    float acc[8][NT];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int c = 0; c < NT; ++c) acc[i][c] = 0.f;
+    const float *xr = xs + (8 * ty) * hop;
+    const float *wr = Ws + tx;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+      float a[8], bb[NT];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = xr[i * hop + k];
+#pragma unroll
+      for (int c = 0; c < NT; ++c) bb[c] = wr[k * NP + 16 * c];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < NT; ++c) acc[i][c] = fmaf(a[i], bb[c], acc[i][c]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ro = r0 + 8 * ty + i;
+      if (ro >= rows_out) continue;
+      float *orow = out + (static_cast<int64_t>(b) * rows_out + ro) * filters;
+#pragma unroll
+      for (int c = 0; c < NT; ++c) {
+        const int n = tx + 16 * c;
+        if (n < filters) orow[n] = activate(acc[i][c] + bv[c], act);
+      }
+    }
+  }
+}
+
+template <int NT>
+static int launch_conv1d_rows(const float *d_x, const float *d_w, const float *d_b, int batch, int rows, int c_in, int taps,
+                              int filters, int stride, int left, int rows_out, int act, float *d_out, size_t smem,
+                              cudaStream_t stream) {
+  SEP_CUDA(cudaFuncSetAttribute(conv1d_rows_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t tiles = static_cast<int64_t>(batch) * ((rows_out + 127) / 128);
+  const int per_sm = std::max(1, std::min(3, static_cast<int>((227 * 1024) / (smem + 1024))));
+  const int grid = static_cast<int>(std::min<int64_t>(tiles, static_cast<int64_t>(sms) * per_sm));
+  profile_begin(stream, "conv1d_rows_kernel<NT=%d> (fp32 SIMT, weights resident in shared memory, 128-row tiles; taps=%d c_in=%d "
+                "filters=%d stride=%d)", NT, taps, c_in, filters, stride);
+  conv1d_rows_kernel<NT><<<grid, 256, smem, stream>>>(d_x, d_w, d_b, batch, rows, c_in, taps, filters, stride, left, rows_out,
+                                                     act, d_out);
+  profile_end(stream);
+  SEP_LAUNCHED();
+  return SEP_OK;
+}
+
 }  // namespace sep
 
 using namespace sep;
@@ -119,6 +218,26 @@ extern "C" int sep_conv1d_f32(const float *x, const float *kernel, const float *
   if ((rc = stage_in(s, bias, static_cast<size_t>(filters), mem, &d_b))) return rc;
   const size_t n_out = static_cast<size_t>(batch) * rows_out * filters;
   if ((rc = stage_out(s, out, n_out, mem, &d_out))) return rc;
+  {
+    // small contraction, many rows: the weights-resident kernel (the reference's Conv1D(129, 2) on [B, K, 40])
+    const int K = taps * c_in, NT = (filters + 15) / 16, hop = stride * c_in;
+    const size_t smem = sizeof(float) * (static_cast<size_t>(K) * 16 * NT + static_cast<size_t>(127) * hop + K + 8);
+    if (NT >= 1 && NT <= 9 && smem <= 100 * 1024 && static_cast<int64_t>(batch) * rows_out >= 4096) {
+      switch (NT) {
+#define SEP_ROWS_CASE(N)                                                                                              \
+  case N:                                                                                                             \
+    rc = launch_conv1d_rows<N>(d_x, d_w, d_b, batch, rows, c_in, taps, filters, stride, left, rows_out, activation,  \
+                               d_out, smem, stream);                                                                  \
+    break;
+        SEP_ROWS_CASE(1) SEP_ROWS_CASE(2) SEP_ROWS_CASE(3) SEP_ROWS_CASE(4) SEP_ROWS_CASE(5)
+        SEP_ROWS_CASE(6) SEP_ROWS_CASE(7) SEP_ROWS_CASE(8) SEP_ROWS_CASE(9)
+#undef SEP_ROWS_CASE
+      }
+      if (rc) return rc;
+      if ((rc = copy_back(s, out, d_out, n_out, mem))) return rc;
+      return finish(s, mem);
+    }
+  }
   dim3 grid((rows_out + kTM - 1) / kTM, (filters + kTN - 1) / kTN, batch);
   profile_begin(stream, "conv1d_kernel (fp32 SIMT, 64x64 tiles; taps=%d c_in=%d filters=%d stride=%d)", taps, c_in, filters, stride);
   conv1d_kernel<<<grid, 256, 0, stream>>>(d_x, d_w, d_b, rows, c_in, taps, filters, stride, left,

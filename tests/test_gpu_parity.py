@@ -642,6 +642,27 @@ def test_conv1d_reference_shape(sep, oracle):
     assert np.max(np.abs(got - ref.numpy())) < 1e-5
 
 
+@pytest.mark.parametrize("batch,rows,c_in,taps,filters,stride,padding,act", [
+    (8, 800, 40, 2, 129, 1, "same", "sigmoid"),      # the reference layer on 4 s utterances: weights-resident kernel
+    (5, 1001, 40, 2, 129, 1, "same", "sigmoid"),     # rows not a multiple of the 128-row tile
+    (3, 4000, 1, 16, 64, 8, "valid", "relu"),        # strided frames (an encoder-shaped call), 4 columns per thread
+    (2, 2500, 7, 5, 33, 2, "same", None),
+])
+def test_conv1d_weights_resident_kernel(sep, oracle, batch, rows, c_in, taps, filters, stride, padding, act):
+    """Calls with >= 4096 output rows and a small contraction take conv1d_rows_kernel (weights resident in shared
+    memory, 128-row tiles); every output against the oracle, and against the generic 64 x 64 kernel on a slice."""
+    rng = np.random.default_rng(rows + filters)
+    x = (0.3 * rng.standard_normal((batch, rows, c_in))).astype(np.float32)
+    w = (0.2 * rng.standard_normal((taps, c_in, filters))).astype(np.float32)
+    bias = (0.1 * rng.standard_normal(filters)).astype(np.float32)
+    got = sep.conv1d(x, w, bias, stride=stride, padding=padding, activation=act)
+    want = oracle.conv1d(x, w, bias, stride=stride, padding=padding, activation=act)
+    assert got.shape == want.shape and np.max(np.abs(got - want)) < 2e-5
+    small = sep.conv1d(x[:1, :300], w, bias, stride=stride, padding=padding, activation=act)     # generic kernel
+    keep = small.shape[1] - taps                      # rows whose receptive field lies inside the slice
+    assert np.max(np.abs(small[0, :keep] - got[0, :keep])) < 1e-5
+
+
 @pytest.mark.parametrize("stride,padding,taps,act", [(1, "valid", 3, "relu"), (2, "same", 5, None),
                                                       (8, "valid", 16, "relu")])
 def test_conv1d_variants(sep, oracle, stride, padding, taps, act):
