@@ -54,6 +54,7 @@ struct sep_plan {
   int bins = 0;     // size/2 + 1
   int half = 0;     // size/2 (length of the complex FFT behind a real one)
   int hops = 0;     // size/shift when divisible, else 0 (no iSTFT / fused path)
+  int pow2 = 1;     // size is a power of two >= 32 (FFT kernels); otherwise only stft / istft run (direct DFT)
   int fading = 1;
   int pad = 0;      // size - shift when fading
   int device = 0;
@@ -68,6 +69,7 @@ struct sep_plan {
   float2 *d_tw_half = nullptr;   // exp(-2 pi i k / half), k < half
   float2 *d_tw_full = nullptr;   // exp(-2 pi i k / size), k <= half
   float2 *d_tw16 = nullptr;      // exp(-2 pi i p*k / 256) [16][16] for the 16x16 FFT
+  float2 *d_tw_n = nullptr;      // exp(-2 pi i k / size), k < size: direct-DFT path of a non-power-of-two size
   // size 256 only: windows as [16 lanes][18] (lane p holds taps p + 16 m at [p*18 + m]; the
   // pitch of 18 makes a half-warp's paired loads conflict-free)
   float *d_win_t = nullptr;      // 0.5 * analysis

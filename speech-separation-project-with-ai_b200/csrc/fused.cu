@@ -330,6 +330,10 @@ static int fused_separate(const sep_plan *p, const float *mix, const float *mask
   SEP_REQUIRE(p->hops > 0 && p->fading,
               "fused path needs size %% shift == 0 and fading (size=%d shift=%d fading=%d)", p->size,
               p->shift, p->fading);
+  if (!p->pow2) {
+    set_error("fused path: size=%d is not a power of two >= 32 (only stft / istft take other sizes)", p->size);
+    return SEP_ERR_UNSUPPORTED;
+  }
   SEP_REQUIRE(refs != nullptr || (scores == nullptr && sums == nullptr),
               "sep_fused_separate_f32: scores/sums need refs");
   SEP_REQUIRE(refs == nullptr || scores != nullptr, "sep_fused_separate_f32: refs given but scores is null");

@@ -407,17 +407,31 @@ __global__ void __launch_bounds__(W * 32, CPS) wstrip512_kernel(const FusedArgs 
         if (!SCORE || !owned) return;
         const float *rf = stage + RING * SHIFT + so[0];             // reference 0 at hop block ta, this lane's pairs
         double e[C][4], r[C][4];
+        if (plain) {                                                // warp-uniform: whole hop block inside [0, n_valid)
 #pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          const int g = gb + 2 * lane + 64 * m;
-          const bool ok0 = plain || (g >= 0 && g < n_valid), ok1 = plain || (g + 1 >= 0 && g + 1 < n_valid);
+          for (int m = 0; m < 2; ++m) {
 #pragma unroll
-          for (int j = 0; j < C; ++j) {
-            const float2 r2 = *reinterpret_cast<const float2 *>(rf + j * RING * SHIFT + 64 * m);
-            r[j][2 * m] = ok0 ? static_cast<double>(r2.x) : 0.0;
-            r[j][2 * m + 1] = ok1 ? static_cast<double>(r2.y) : 0.0;
-            e[j][2 * m] = ok0 ? static_cast<double>(yo[j][m].x) : 0.0;
-            e[j][2 * m + 1] = ok1 ? static_cast<double>(yo[j][m].y) : 0.0;
+            for (int j = 0; j < C; ++j) {
+              const float2 r2 = *reinterpret_cast<const float2 *>(rf + j * RING * SHIFT + 64 * m);
+              r[j][2 * m] = static_cast<double>(r2.x);
+              r[j][2 * m + 1] = static_cast<double>(r2.y);
+              e[j][2 * m] = static_cast<double>(yo[j][m].x);
+              e[j][2 * m + 1] = static_cast<double>(yo[j][m].y);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int m = 0; m < 2; ++m) {
+            const int g = gb + 2 * lane + 64 * m;
+            const bool ok0 = g >= 0 && g < n_valid, ok1 = g + 1 >= 0 && g + 1 < n_valid;
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+              const float2 r2 = *reinterpret_cast<const float2 *>(rf + j * RING * SHIFT + 64 * m);
+              r[j][2 * m] = ok0 ? static_cast<double>(r2.x) : 0.0;
+              r[j][2 * m + 1] = ok1 ? static_cast<double>(r2.y) : 0.0;
+              e[j][2 * m] = ok0 ? static_cast<double>(yo[j][m].x) : 0.0;
+              e[j][2 * m + 1] = ok1 ? static_cast<double>(yo[j][m].y) : 0.0;
+            }
           }
         }
 #pragma unroll

@@ -114,6 +114,57 @@ __global__ void istft_kernel(const float2 *__restrict__ spec, const float *__res
   }
 }
 
+// Any size with size % shift == 0: inverse real DFT by direct summation (numpy's irfft: the imaginary parts of DC and,
+// for even sizes, of the Nyquist bin are ignored), synthesis window, the same frame-ordered overlap-add.
+__global__ void istft_dft_kernel(const float2 *__restrict__ spec, int T, int size, int shift, int pad, int tb,
+                                 int64_t out_len, const float *__restrict__ syn, const float2 *__restrict__ tw_n,
+                                 float *__restrict__ wave) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int F = size / 2 + 1, R = size / shift;
+  const int b = blockIdx.y;
+  const int j_lo = pad / shift, j_hi = T + R - 1 - j_lo;
+  const int j0 = max(blockIdx.x * tb, j_lo), j1 = min((blockIdx.x + 1) * tb, j_hi);
+  if (j0 >= j1) return;
+  const int t_lo = max(j0 - R + 1, 0), t_hi = min(j1, T);
+  const int nframes = t_hi - t_lo, slots = tb + R - 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  float *fb = reinterpret_cast<float *>(smem_raw);                         // [slots][size]
+  float2 *tw = reinterpret_cast<float2 *>(fb + static_cast<size_t>(slots) * size);
+  float2 *Y = tw + size + static_cast<size_t>(warp) * F;
+  for (int i = threadIdx.x; i < size; i += blockDim.x) tw[i] = tw_n[i];
+  __syncthreads();
+  const bool even = (size & 1) == 0;
+  const int kmax = even ? size / 2 - 1 : size / 2;                          // bins 1..kmax count twice
+  for (int f = warp; f < nframes; f += nwarps) {
+    const int64_t frame = static_cast<int64_t>(b) * T + t_lo + f;
+    for (int k = lane; k < F; k += 32) Y[k] = __ldg(spec + frame * F + k);
+    __syncwarp();
+    for (int m = lane; m < size; m += 32) {
+      float acc = Y[0].x;
+      if (even) acc += (m & 1) ? -Y[size / 2].x : Y[size / 2].x;
+      int idx = 0;
+      for (int k = 1; k <= kmax; ++k) {
+        idx += m;
+        if (idx >= size) idx -= size;
+        const float2 w = tw[idx];                                          // (cos, -sin) of 2 pi k m / n
+        acc = fmaf(2.f * Y[k].x, w.x, acc);                                // Re(Y e^{+i theta}) = Yr cos - Yi sin
+        acc = fmaf(2.f * Y[k].y, w.y, acc);
+      }
+      fb[static_cast<size_t>(f) * size + m] = acc * syn[m];
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  const int span = (j1 - j0) * shift;
+  float *out = wave + static_cast<int64_t>(b) * out_len;
+  for (int i = threadIdx.x; i < span; i += blockDim.x) {
+    const int j = j0 + i / shift, m = i % shift;
+    float acc = 0.f;
+    for (int t = max(j - R + 1, t_lo); t <= min(j, t_hi - 1); ++t) acc += fb[(t - t_lo) * size + (j - t) * shift + m];
+    out[static_cast<int64_t>(j) * shift + m - pad] = acc;
+  }
+}
+
 template <int MODE>
 static int launch_istft(const sep_plan *p, const float *in0, const float *in1, int batch, int n_src,
                         int frames, float *wave, int mem, cudaStream_t stream) {
@@ -124,6 +175,36 @@ static int launch_istft(const sep_plan *p, const float *in0, const float *in1, i
   int64_t L = 0;
   sep_plan_istft_samples(p, frames, &L);
   if (L == 0 || frames == 0) return SEP_OK;
+  if (!p->pow2) {
+    if (MODE != 0) {
+      set_error("recombine_istft: size=%d is not a power of two >= 32 (only stft / istft take other sizes)", p->size);
+      return SEP_ERR_UNSUPPORTED;
+    }
+    const int warps = 4, tb = 8;
+    Scratch s(stream);
+    const float *d0;
+    float *d_wave;
+    const size_t TF = static_cast<size_t>(batch) * frames * p->bins;
+    if ((rc = stage_in(s, in0, TF * 2, mem, &d0))) return rc;
+    const size_t out_count = static_cast<size_t>(batch) * L;
+    if ((rc = stage_out(s, wave, out_count, mem, &d_wave))) return rc;
+    const size_t smem = static_cast<size_t>(tb + p->hops - 1) * p->size * sizeof(float) + p->size * sizeof(float2) +
+                        static_cast<size_t>(warps) * p->bins * sizeof(float2) + 16;
+    if (smem > 200 * 1024) {
+      set_error("istft: size=%d shift=%d does not fit in shared memory (direct-DFT path)", p->size, p->shift);
+      return SEP_ERR_UNSUPPORTED;
+    }
+    SEP_CUDA(cudaFuncSetAttribute(istft_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const int j_hi = frames + p->hops - 1 - p->pad / p->shift;
+    dim3 grid((j_hi + tb - 1) / tb, batch);
+    profile_begin(stream, "istft_dft_kernel (direct inverse DFT, size=%d)", p->size);
+    istft_dft_kernel<<<grid, warps * 32, smem, stream>>>(reinterpret_cast<const float2 *>(d0), frames, p->size, p->shift,
+                                                         p->pad, tb, L, p->d_syn, p->d_tw_n, d_wave);
+    profile_end(stream);
+    SEP_LAUNCHED();
+    if ((rc = copy_back(s, wave, d_wave, out_count, mem))) return rc;
+    return finish(s, mem);
+  }
   OlaCfg cfg;
   if (!pick_ola(p, n_src, MODE == 1 ? p->bins : 0, &cfg)) {
     set_error("istft: size=%d shift=%d sources=%d does not fit in shared memory", p->size, p->shift,

@@ -130,8 +130,8 @@ int sep_profile_collect(double *total_ms, int *launches) {
 int sep_plan_create(sep_plan **out, int size, int shift, const double *window, int fading) {
   SEP_REQUIRE(out != nullptr && window != nullptr, "sep_plan_create: null argument");
   *out = nullptr;
-  if (size < 32 || size > 4096 || (size & (size - 1)) != 0) {
-    set_error("sep_plan_create: size=%d unsupported (power of two in [32, 4096] required)", size);
+  if (size < 2 || size > 4096) {
+    set_error("sep_plan_create: size=%d unsupported (2 <= size <= 4096)", size);
     return SEP_ERR_UNSUPPORTED;
   }
   SEP_REQUIRE(shift >= 1 && shift <= size, "sep_plan_create: shift=%d must be in [1, size=%d]",
@@ -142,6 +142,9 @@ int sep_plan_create(sep_plan **out, int size, int shift, const double *window, i
     return SEP_ERR_NOMEM;
   }
   p->size = size;
+  // FFT kernels need a power of two >= 32; any other size (the reference's `size` is free, parallel_stft.py:146)
+  // runs the direct-DFT kernels of stft / istft -- a compatibility path, O(size^2) per frame
+  p->pow2 = size >= 32 && (size & (size - 1)) == 0 ? 1 : 0;
   p->shift = shift;
   p->half = size / 2;
   p->bins = size / 2 + 1;
@@ -216,6 +219,12 @@ int sep_plan_create(sep_plan **out, int size, int shift, const double *window, i
     if ((rc = upload(&p->d_tw_half, th)) != SEP_OK) break;
     if ((rc = upload(&p->d_tw_full, tf)) != SEP_OK) break;
     if ((rc = upload(&p->d_tw16, t16)) != SEP_OK) break;
+    if (!p->pow2) {
+      std::vector<float2> tn(n);
+      for (int k = 0; k < n; ++k)
+        tn[k] = make_float2(static_cast<float>(std::cos(two_pi * k / n)), static_cast<float>(-std::sin(two_pi * k / n)));
+      if ((rc = upload(&p->d_tw_n, tn)) != SEP_OK) break;
+    }
     if (size == 256) {
       std::vector<float> wt(16 * 18 + 8, 0.f), st(16 * 18 + 8, 0.f);
       for (int lane = 0; lane < 16; ++lane)
@@ -259,6 +268,7 @@ int sep_plan_destroy(sep_plan *p) {
   cudaFree(p->d_tw_half);
   cudaFree(p->d_tw_full);
   cudaFree(p->d_tw16);
+  cudaFree(p->d_tw_n);
   cudaFree(p->d_win_t);
   cudaFree(p->d_syn_t);
   cudaFree(p->d_win2_t);

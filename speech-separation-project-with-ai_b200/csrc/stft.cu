@@ -69,6 +69,45 @@ __global__ void stft_kernel(const float *__restrict__ wave, int64_t n, int64_t s
   }
 }
 
+// Any size (parallel_stft.py:146 takes a free `size`; every call site of the reference uses 256): the real DFT of a
+// windowed frame by direct summation, X[k] = sum_m xw[m] W_n^(k m), k <= n / 2 -- O(n^2) per frame, the twiddle index
+// walks the table modulo n without a division.  A compatibility path, not a hot path.
+__global__ void stft_dft_kernel(const float *__restrict__ wave, int64_t n, int64_t stride, int T, int size, int shift,
+                                int pad, int frames_per_tile, const float *__restrict__ win_full,
+                                const float2 *__restrict__ tw_n, float2 *__restrict__ spec) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int F = size / 2 + 1;
+  const int b = blockIdx.y, t0 = blockIdx.x * frames_per_tile;
+  const int nframes = min(frames_per_tile, T - t0);
+  const int tile_cap = (frames_per_tile - 1) * shift + size;
+  const int tile_len = (nframes - 1) * shift + size;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  float *tile = reinterpret_cast<float *>(smem_raw);
+  float2 *tw = reinterpret_cast<float2 *>(tile + ((tile_cap + 3) & ~3));
+  float *xw = reinterpret_cast<float *>(tw + size) + static_cast<size_t>(warp) * size;
+  stage_wave(tile, wave + static_cast<int64_t>(b) * stride, n, static_cast<int64_t>(t0) * shift - pad, tile_len);
+  for (int i = threadIdx.x; i < size; i += blockDim.x) tw[i] = tw_n[i];
+  __syncthreads();
+  for (int f = warp; f < nframes; f += nwarps) {
+    for (int m = lane; m < size; m += 32) xw[m] = tile[f * shift + m] * win_full[m];
+    __syncwarp();
+    float2 *row = spec + (static_cast<int64_t>(b) * T + t0 + f) * F;
+    for (int k = lane; k < F; k += 32) {
+      float re = 0.f, im = 0.f;
+      int idx = 0;
+      for (int m = 0; m < size; ++m) {
+        const float2 w = tw[idx];
+        re = fmaf(xw[m], w.x, re);
+        im = fmaf(xw[m], w.y, im);
+        idx += k;
+        if (idx >= size) idx -= size;
+      }
+      row[k] = make_float2(re, im);
+    }
+    __syncwarp();
+  }
+}
+
 // feats [B, T, 2F] = |X| || angle X ; labels [B, T, C*F] = |S_c| cos(angle X - angle S_c).
 __global__ void features_kernel(const float *__restrict__ mix, const float *__restrict__ refs,
                                 int n_src, int64_t n, int T, int size, int shift, int pad,
@@ -186,6 +225,21 @@ int sep_stft_f32(const sep_plan *p, const float *wave, int batch, int64_t n_samp
   if ((rc = stage_in(s, wave, static_cast<size_t>(batch) * wave_stride, mem, &d_wave))) return rc;
   const size_t out_count = static_cast<size_t>(batch) * T * p->bins * 2;
   if ((rc = stage_out(s, spec, out_count, mem, &d_spec))) return rc;
+  if (!p->pow2) {
+    const int warps = 4, frames = 8;
+    const size_t smem = (((frames - 1) * static_cast<size_t>(p->shift) + p->size + 3) & ~size_t(3)) * sizeof(float) +
+                        p->size * sizeof(float2) + static_cast<size_t>(warps) * p->size * sizeof(float) + 16;
+    SEP_CUDA(cudaFuncSetAttribute(stft_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    dim3 grid((T + frames - 1) / frames, batch);
+    profile_begin(stream, "stft_dft_kernel (direct DFT, size=%d)", p->size);
+    stft_dft_kernel<<<grid, warps * 32, smem, stream>>>(d_wave, n_samples, wave_stride, T, p->size, p->shift, p->pad,
+                                                        frames, p->d_win_full, p->d_tw_n,
+                                                        reinterpret_cast<float2 *>(d_spec));
+    profile_end(stream);
+    SEP_LAUNCHED();
+    if ((rc = copy_back(s, spec, d_spec, out_count, mem))) return rc;
+    return finish(s, mem);
+  }
   const TileCfg cfg = pick_tile(p, 1, 0);
   SEP_CUDA(cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(cfg.smem + 16)));
@@ -208,6 +262,10 @@ int sep_stft_features_f32(const sep_plan *p, const float *mix, const float *refs
   SEP_REQUIRE(n_src == 0 || refs != nullptr, "sep_stft_features_f32: refs required when n_src > 0");
   SEP_REQUIRE(labels == nullptr || n_src > 0, "sep_stft_features_f32: labels need n_src > 0");
   SEP_REQUIRE(batch >= 1 && n_samples >= 0, "sep_stft_features_f32: bad shape");
+  if (!p->pow2) {
+    set_error("sep_stft_features_f32: size=%d is not a power of two >= 32 (only stft / istft take other sizes)", p->size);
+    return SEP_ERR_UNSUPPORTED;
+  }
   int rc = check_mem(mem);
   if (rc) return rc;
   int T = 0;

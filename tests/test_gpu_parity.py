@@ -82,9 +82,29 @@ def test_stft_edge_lengths(sep, oracle):
     assert got.shape == want.shape and rel_err(got, want) < TOL_REL
 
 
-def test_stft_unsupported_size_fails_loudly(sep):
+def test_stft_istft_any_size(sep, oracle):
+    """`size` is free in the reference (parallel_stft.py:146, cell 39); sizes that are not a power of two >= 32 run the
+    direct-DFT kernels: same results as the oracle, round trip included.  The fused path stays power-of-two only and
+    says so loudly."""
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal(3000).astype(np.float32)
+    for size, shift, win in ((200, 100, windows.blackman), (250, 50, windows.hann), (30, 10, windows.hamming),
+                             (129, 43, windows.blackman), (16, 4, windows.hann)):
+        got = sep.stft(x, time_dim=0, size=size, shift=shift, window=win)
+        want = oracle.stft(x, time_dim=0, size=size, shift=shift, window=win)
+        assert got.shape == want.shape and rel_err(got, want) < TOL_REL, size
+        back = sep.istft(want, size=size, shift=shift, window=win)
+        want_back = oracle.istft(want, size=size, shift=shift, window=win)
+        assert back.shape == want_back.shape and rel_err(back, want_back) < TOL_REL, size
+        assert rel_err(back[:len(x)], x) < 1e-3, size                      # perfect reconstruction up to fp32
+    # batched input through the same path
+    xb = rng.standard_normal((3, 1000)).astype(np.float32)
+    got = sep.stft(xb, size=200, shift=100)
+    for i in range(3):
+        assert rel_err(got[i], oracle.stft(xb[i], time_dim=0, size=200, shift=100)) < TOL_REL
     with pytest.raises(NotImplementedError):
-        sep.stft(np.zeros(1000, np.float32), time_dim=0, size=200, shift=100)
+        sep.separate_and_score(np.zeros((1, 1000), np.float32), np.zeros((1, 1, sep.get_plan(200, 100).frames(1000), 101),
+                               np.float32), None, size=200, shift=100)
 
 
 def test_stft_against_tfrecord_golden(sep, wsj0, tfrecord_golden):
