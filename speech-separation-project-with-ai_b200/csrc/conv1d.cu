@@ -166,6 +166,131 @@ conv1d_rows_kernel(const float *__restrict__ x, const float *__restrict__ w, con
   }
 }
 
+// The reference layer itself: 129 filters = one block of 128 columns + a ragged tail of REM <= 8 columns.  A thread owns
+// 8 rows x 8 CONTIGUOUS columns (weights as two LDS.128, activations as LDS.128 over four k at a time: 16 shared loads
+// per 256 FFMAs), and the tail columns are spread over the threads (row 8 ty + tx / 2 ... one row each) instead of
+// wasting a ninth strided column slot on every thread.  Needs stride * c_in and K to be multiples of 4.
+template <int REM>
+__global__ void __launch_bounds__(256)
+conv1d_rows128_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
+                      int batch, int rows, int c_in, int taps, int filters, int stride, int left, int rows_out,
+                      int act, float *__restrict__ out) {
+  extern __shared__ __align__(16) float smem_f[];
+  constexpr int RT = 128, NP = 128 + 8;
+  const int K = taps * c_in, hop = stride * c_in;
+  const int span = (RT - 1) * hop + K;
+  float *Ws = smem_f;                                       // [K][136]: columns 0..127, then the tail (zero padded)
+  float *xs = smem_f + K * NP;
+  for (int e = threadIdx.x; e < K * NP; e += 256) {
+    const int k = e / NP, n = e - k * NP;
+    Ws[e] = n < filters ? __ldg(w + static_cast<int64_t>(k) * filters + n) : 0.f;
+  }
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float bv[8], bt[REM];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) bv[c] = bias ? __ldg(bias + 8 * tx + c) : 0.f;
+#pragma unroll
+  for (int c = 0; c < REM; ++c) bt[c] = (bias && 128 + c < filters) ? __ldg(bias + 128 + c) : 0.f;
+  const int tiles_per = (rows_out + RT - 1) / RT, tiles = batch * tiles_per;
+  for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const int b = t / tiles_per, r0 = (t - b * tiles_per) * RT;
+    const float *xb = x + static_cast<int64_t>(b) * rows * c_in;
+    const int64_t g0 = static_cast<int64_t>(r0 * stride - left) * c_in;
+    const int64_t n_x = static_cast<int64_t>(rows) * c_in;
+    __syncthreads();
+    if (g0 >= 0 && g0 + span <= n_x && (reinterpret_cast<uintptr_t>(xb + g0) & 15) == 0) {
+      for (int e = threadIdx.x; e < span / 4; e += 256)
+        reinterpret_cast<float4 *>(xs)[e] = __ldg(reinterpret_cast<const float4 *>(xb + g0) + e);
+    } else {
+      for (int e = threadIdx.x; e < span; e += 256) {
+        const int64_t g = g0 + e;
+        xs[e] = (g >= 0 && g < n_x) ? __ldg(xb + g) : 0.f;
+      }
+    }
+    __syncthreads();
+    float acc[8][8], tail[REM];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
+#pragma unroll
+    for (int c = 0; c < REM; ++c) tail[c] = 0.f;
+    const float *xr = xs + (8 * ty) * hop;
+    const float *wr = Ws + 8 * tx;
+    const float *xt = xs + (8 * ty + (tx >> 1)) * hop;      // the tail row of this thread (threads with even tx)
+    for (int k = 0; k < K; k += 4) {
+      float4 a4[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a4[i] = *reinterpret_cast<const float4 *>(xr + i * hop + k);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const float4 b0 = *reinterpret_cast<const float4 *>(wr + (k + kk) * NP);
+        const float4 b1 = *reinterpret_cast<const float4 *>(wr + (k + kk) * NP + 4);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float av = kk == 0 ? a4[i].x : kk == 1 ? a4[i].y : kk == 2 ? a4[i].z : a4[i].w;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[i][c] = fmaf(av, bb[c], acc[i][c]);
+        }
+      }
+      if ((tx & 1) == 0) {
+        const float4 av = *reinterpret_cast<const float4 *>(xt + k);
+        const float a[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+          for (int c = 0; c < REM; ++c) tail[c] = fmaf(a[kk], Ws[(k + kk) * NP + 128 + c], tail[c]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ro = r0 + 8 * ty + i;
+      if (ro >= rows_out) continue;
+      float *orow = out + (static_cast<int64_t>(b) * rows_out + ro) * filters + 8 * tx;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) orow[c] = activate(acc[i][c] + bv[c], act);
+    }
+    if ((tx & 1) == 0) {
+      const int ro = r0 + 8 * ty + (tx >> 1);
+      if (ro < rows_out) {
+        float *orow = out + (static_cast<int64_t>(b) * rows_out + ro) * filters + 128;
+#pragma unroll
+        for (int c = 0; c < REM; ++c)
+          if (128 + c < filters) orow[c] = activate(tail[c] + bt[c], act);
+      }
+    }
+  }
+}
+
+static int launch_conv1d_rows128(const float *d_x, const float *d_w, const float *d_b, int batch, int rows, int c_in,
+                                 int taps, int filters, int stride, int left, int rows_out, int act, float *d_out,
+                                 cudaStream_t stream) {
+  const int K = taps * c_in, hop = stride * c_in;
+  const size_t smem = sizeof(float) * (static_cast<size_t>(K) * 136 + static_cast<size_t>(127) * hop + K + 8);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t tiles = static_cast<int64_t>(batch) * ((rows_out + 127) / 128);
+  const int per_sm = std::max(1, std::min(3, static_cast<int>((227 * 1024) / (smem + 1024))));
+  const int grid = static_cast<int>(std::min<int64_t>(tiles, static_cast<int64_t>(sms) * per_sm));
+  const int rem = filters - 128;
+  profile_begin(stream, "conv1d_rows128_kernel<REM=%d> (fp32 SIMT, weights resident in shared memory, 128-row tiles, 8 x 8 "
+                "micro-tiles; taps=%d c_in=%d filters=%d stride=%d)", rem <= 1 ? 1 : 8, taps, c_in, filters, stride);
+  if (rem <= 1) {
+    SEP_CUDA(cudaFuncSetAttribute(conv1d_rows128_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    conv1d_rows128_kernel<1><<<grid, 256, smem, stream>>>(d_x, d_w, d_b, batch, rows, c_in, taps, filters, stride, left,
+                                                          rows_out, act, d_out);
+  } else {
+    SEP_CUDA(cudaFuncSetAttribute(conv1d_rows128_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    conv1d_rows128_kernel<8><<<grid, 256, smem, stream>>>(d_x, d_w, d_b, batch, rows, c_in, taps, filters, stride, left,
+                                                          rows_out, act, d_out);
+  }
+  profile_end(stream);
+  SEP_LAUNCHED();
+  return SEP_OK;
+}
+
 template <int NT>
 static int launch_conv1d_rows(const float *d_x, const float *d_w, const float *d_b, int batch, int rows, int c_in, int taps,
                               int filters, int stride, int left, int rows_out, int act, float *d_out, size_t smem,
@@ -222,7 +347,16 @@ extern "C" int sep_conv1d_f32(const float *x, const float *kernel, const float *
     // small contraction, many rows: the weights-resident kernel (the reference's Conv1D(129, 2) on [B, K, 40])
     const int K = taps * c_in, NT = (filters + 15) / 16, hop = stride * c_in;
     const size_t smem = sizeof(float) * (static_cast<size_t>(K) * 16 * NT + static_cast<size_t>(127) * hop + K + 8);
-    if (NT >= 1 && NT <= 9 && smem <= 100 * 1024 && static_cast<int64_t>(batch) * rows_out >= 4096) {
+    const bool big = static_cast<int64_t>(batch) * rows_out >= 4096;
+    if (big && filters >= 128 && filters <= 136 && K % 4 == 0 && hop % 4 == 0 &&
+        sizeof(float) * (static_cast<size_t>(K) * 136 + static_cast<size_t>(127) * hop + K + 8) <= 100 * 1024) {
+      if ((rc = launch_conv1d_rows128(d_x, d_w, d_b, batch, rows, c_in, taps, filters, stride, left, rows_out, activation,
+                                      d_out, stream)))
+        return rc;
+      if ((rc = copy_back(s, out, d_out, n_out, mem))) return rc;
+      return finish(s, mem);
+    }
+    if (NT >= 1 && NT <= 9 && smem <= 100 * 1024 && big) {
       switch (NT) {
 #define SEP_ROWS_CASE(N)                                                                                              \
   case N:                                                                                                             \

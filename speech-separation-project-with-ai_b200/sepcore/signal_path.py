@@ -249,6 +249,10 @@ def istft(stft_signal, size=1024, shift=256, window=None, fading=True, window_le
     """
     assert stft_signal.shape[-1] == size // 2 + 1
     assert size % shift == 0        # cell 38 :1245
+    if size % 2:
+        # the reference's `irfft(stft_signal[j])` (:1301, no `n`) returns 2 (F - 1) = size - 1 samples for an odd size,
+        # and adding them to a `size`-long window product raises exactly this numpy error
+        raise ValueError("operands could not be broadcast together with shapes (%d,) (%d,) " % (size, size - 1))
     plan = get_plan(size, shift, window, fading, window_length)
     lib = _lib.load()
     dev = is_device_tensor(stft_signal)

@@ -93,10 +93,18 @@ def test_stft_istft_any_size(sep, oracle):
         got = sep.stft(x, time_dim=0, size=size, shift=shift, window=win)
         want = oracle.stft(x, time_dim=0, size=size, shift=shift, window=win)
         assert got.shape == want.shape and rel_err(got, want) < TOL_REL, size
+        if size % 2:
+            # an odd size breaks the reference's own istft (irfft without n gives size - 1 samples): same error here
+            with pytest.raises(ValueError):
+                oracle.istft(want, size=size, shift=shift, window=win)
+            with pytest.raises(ValueError):
+                sep.istft(want, size=size, shift=shift, window=win)
+            continue
         back = sep.istft(want, size=size, shift=shift, window=win)
         want_back = oracle.istft(want, size=size, shift=shift, window=win)
         assert back.shape == want_back.shape and rel_err(back, want_back) < TOL_REL, size
-        assert rel_err(back[:len(x)], x) < 1e-3, size                      # perfect reconstruction up to fp32
+        if win is not windows.hamming:                 # (the `index + 1 < size` quirk of cell 38 costs Hamming 0.4 %)
+            assert rel_err(back[:len(x)], x) < 1e-3, size                  # perfect reconstruction up to fp32
     # batched input through the same path
     xb = rng.standard_normal((3, 1000)).astype(np.float32)
     got = sep.stft(xb, size=200, shift=100)
@@ -667,6 +675,7 @@ def test_conv1d_reference_shape(sep, oracle):
     (5, 1001, 40, 2, 129, 1, "same", "sigmoid"),     # rows not a multiple of the 128-row tile
     (3, 4000, 1, 16, 64, 8, "valid", "relu"),        # strided frames (an encoder-shaped call), 4 columns per thread
     (2, 2500, 7, 5, 33, 2, "same", None),
+    (4, 1200, 8, 4, 134, 2, "same", "relu"),         # 128 + 6 tail columns: the 8 x 8 micro-tile kernel with REM = 8
 ])
 def test_conv1d_weights_resident_kernel(sep, oracle, batch, rows, c_in, taps, filters, stride, padding, act):
     """Calls with >= 4096 output rows and a small contraction take conv1d_rows_kernel (weights resident in shared
