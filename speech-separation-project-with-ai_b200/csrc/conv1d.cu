@@ -13,6 +13,7 @@
 // through shared memory 16 at a time.  (The tcgen05 variant for the BASELINE
 // N=256/L=16 shape is tracked in DESIGN.md.)
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -167,9 +168,11 @@ conv1d_rows_kernel(const float *__restrict__ x, const float *__restrict__ w, con
 }
 
 // The reference layer itself: 129 filters = one block of 128 columns + a ragged tail of REM <= 8 columns.  A thread owns
-// 8 rows x 8 CONTIGUOUS columns (weights as two LDS.128, activations as LDS.128 over four k at a time: 16 shared loads
-// per 256 FFMAs), and the tail columns are spread over the threads (row 8 ty + tx / 2 ... one row each) instead of
-// wasting a ninth strided column slot on every thread.  Needs stride * c_in and K to be multiples of 4.
+// 8 rows x 8 columns tx + 16 c (so that the 16 threads of a row group store 16 consecutive floats: coalesced), but the
+// weights sit PERMUTED in shared memory -- column tx + 16 c at 4 tx + c (c < 4) / 64 + 4 tx + c - 4 -- so the thread's
+// eight weights of a k are two conflict-free LDS.128; activations are LDS.128 over four k at a time: 16 shared loads per
+// 256 FFMAs.  The tail columns are spread over the threads (one row each for every second thread) instead of wasting a
+// ninth strided column slot on every thread.  Needs stride * c_in and K to be multiples of 4.
 template <int REM>
 __global__ void __launch_bounds__(256)
 conv1d_rows128_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
@@ -179,16 +182,21 @@ conv1d_rows128_kernel(const float *__restrict__ x, const float *__restrict__ w, 
   constexpr int RT = 128, NP = 128 + 8;
   const int K = taps * c_in, hop = stride * c_in;
   const int span = (RT - 1) * hop + K;
-  float *Ws = smem_f;                                       // [K][136]: columns 0..127, then the tail (zero padded)
+  float *Ws = smem_f;                                       // [K][136]: columns 0..127 permuted, then the tail (zero padded)
   float *xs = smem_f + K * NP;
   for (int e = threadIdx.x; e < K * NP; e += 256) {
     const int k = e / NP, n = e - k * NP;
-    Ws[e] = n < filters ? __ldg(w + static_cast<int64_t>(k) * filters + n) : 0.f;
+    int pos = n;
+    if (n < 128) {
+      const int t = n & 15, c = n >> 4;                     // column n = t + 16 c
+      pos = c < 4 ? 4 * t + c : 64 + 4 * t + (c - 4);
+    }
+    Ws[k * NP + pos] = n < filters ? __ldg(w + static_cast<int64_t>(k) * filters + n) : 0.f;
   }
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float bv[8], bt[REM];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) bv[c] = bias ? __ldg(bias + 8 * tx + c) : 0.f;
+  for (int c = 0; c < 8; ++c) bv[c] = bias ? __ldg(bias + tx + 16 * c) : 0.f;
 #pragma unroll
   for (int c = 0; c < REM; ++c) bt[c] = (bias && 128 + c < filters) ? __ldg(bias + 128 + c) : 0.f;
   const int tiles_per = (rows_out + RT - 1) / RT, tiles = batch * tiles_per;
@@ -216,7 +224,7 @@ conv1d_rows128_kernel(const float *__restrict__ x, const float *__restrict__ w, 
 #pragma unroll
     for (int c = 0; c < REM; ++c) tail[c] = 0.f;
     const float *xr = xs + (8 * ty) * hop;
-    const float *wr = Ws + 8 * tx;
+    const float *wr = Ws + 4 * tx;
     const float *xt = xs + (8 * ty + (tx >> 1)) * hop;      // the tail row of this thread (threads with even tx)
     for (int k = 0; k < K; k += 4) {
       float4 a4[8];
@@ -225,7 +233,7 @@ conv1d_rows128_kernel(const float *__restrict__ x, const float *__restrict__ w, 
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         const float4 b0 = *reinterpret_cast<const float4 *>(wr + (k + kk) * NP);
-        const float4 b1 = *reinterpret_cast<const float4 *>(wr + (k + kk) * NP + 4);
+        const float4 b1 = *reinterpret_cast<const float4 *>(wr + (k + kk) * NP + 64);
         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -247,9 +255,9 @@ conv1d_rows128_kernel(const float *__restrict__ x, const float *__restrict__ w, 
     for (int i = 0; i < 8; ++i) {
       const int ro = r0 + 8 * ty + i;
       if (ro >= rows_out) continue;
-      float *orow = out + (static_cast<int64_t>(b) * rows_out + ro) * filters + 8 * tx;
+      float *orow = out + (static_cast<int64_t>(b) * rows_out + ro) * filters + tx;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) orow[c] = activate(acc[i][c] + bv[c], act);
+      for (int c = 0; c < 8; ++c) orow[16 * c] = activate(acc[i][c] + bv[c], act);
     }
     if ((tx & 1) == 0) {
       const int ro = r0 + 8 * ty + (tx >> 1);
@@ -272,17 +280,23 @@ static int launch_conv1d_rows128(const float *d_x, const float *d_w, const float
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t tiles = static_cast<int64_t>(batch) * ((rows_out + 127) / 128);
-  const int per_sm = std::max(1, std::min(3, static_cast<int>((227 * 1024) / (smem + 1024))));
-  const int grid = static_cast<int>(std::min<int64_t>(tiles, static_cast<int64_t>(sms) * per_sm));
   const int rem = filters - 128;
+  // persistent grid = exactly the CTAs that are resident at once (a larger grid would run a second, half-empty wave)
+  int per_sm = 1;
+  if (rem <= 1) {
+    SEP_CUDA(cudaFuncSetAttribute(conv1d_rows128_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    SEP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv1d_rows128_kernel<1>, 256, smem));
+  } else {
+    SEP_CUDA(cudaFuncSetAttribute(conv1d_rows128_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    SEP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv1d_rows128_kernel<8>, 256, smem));
+  }
+  const int grid = static_cast<int>(std::min<int64_t>(tiles, static_cast<int64_t>(sms) * std::max(per_sm, 1)));
   profile_begin(stream, "conv1d_rows128_kernel<REM=%d> (fp32 SIMT, weights resident in shared memory, 128-row tiles, 8 x 8 "
                 "micro-tiles; taps=%d c_in=%d filters=%d stride=%d)", rem <= 1 ? 1 : 8, taps, c_in, filters, stride);
   if (rem <= 1) {
-    SEP_CUDA(cudaFuncSetAttribute(conv1d_rows128_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     conv1d_rows128_kernel<1><<<grid, 256, smem, stream>>>(d_x, d_w, d_b, batch, rows, c_in, taps, filters, stride, left,
                                                           rows_out, act, d_out);
   } else {
-    SEP_CUDA(cudaFuncSetAttribute(conv1d_rows128_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     conv1d_rows128_kernel<8><<<grid, 256, smem, stream>>>(d_x, d_w, d_b, batch, rows, c_in, taps, filters, stride, left,
                                                           rows_out, act, d_out);
   }
@@ -300,8 +314,9 @@ static int launch_conv1d_rows(const float *d_x, const float *d_w, const float *d
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t tiles = static_cast<int64_t>(batch) * ((rows_out + 127) / 128);
-  const int per_sm = std::max(1, std::min(3, static_cast<int>((227 * 1024) / (smem + 1024))));
-  const int grid = static_cast<int>(std::min<int64_t>(tiles, static_cast<int64_t>(sms) * per_sm));
+  int per_sm = 1;
+  SEP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv1d_rows_kernel<NT>, 256, smem));
+  const int grid = static_cast<int>(std::min<int64_t>(tiles, static_cast<int64_t>(sms) * std::max(per_sm, 1)));
   profile_begin(stream, "conv1d_rows_kernel<NT=%d> (fp32 SIMT, weights resident in shared memory, 128-row tiles; taps=%d c_in=%d "
                 "filters=%d stride=%d)", NT, taps, c_in, filters, stride);
   conv1d_rows_kernel<NT><<<grid, 256, smem, stream>>>(d_x, d_w, d_b, batch, rows, c_in, taps, filters, stride, left, rows_out,
@@ -310,6 +325,10 @@ static int launch_conv1d_rows(const float *d_x, const float *d_w, const float *d
   SEP_LAUNCHED();
   return SEP_OK;
 }
+
+int conv1d_tc_try(const float *d_x, const float *d_w, const float *d_b, int batch, int rows, int c_in, int taps,
+                  int filters, int stride, int left, int rows_out, int act, float *d_out, cudaStream_t stream,
+                  bool *handled);
 
 }  // namespace sep
 
@@ -343,6 +362,20 @@ extern "C" int sep_conv1d_f32(const float *x, const float *kernel, const float *
   if ((rc = stage_in(s, bias, static_cast<size_t>(filters), mem, &d_b))) return rc;
   const size_t n_out = static_cast<size_t>(batch) * rows_out * filters;
   if ((rc = stage_out(s, out, n_out, mem, &d_out))) return rc;
+  // the reference layer over a dataset shard: 3xTF32 on the tensor cores (conv1d_tc.cu); SEPCORE_CONV_SIMT=1 keeps the
+  // exact-fp32 SIMT kernels below (the cross-check)
+  const char *simt_env = getenv("SEPCORE_CONV_SIMT");
+  const bool simt_only = simt_env && atoi(simt_env) != 0;
+  if (!simt_only) {
+    bool handled = false;
+    if ((rc = conv1d_tc_try(d_x, d_w, d_b, batch, rows, c_in, taps, filters, stride, left, rows_out, activation, d_out,
+                            stream, &handled)))
+      return rc;
+    if (handled) {
+      if ((rc = copy_back(s, out, d_out, n_out, mem))) return rc;
+      return finish(s, mem);
+    }
+  }
   {
     // small contraction, many rows: the weights-resident kernel (the reference's Conv1D(129, 2) on [B, K, 40])
     const int K = taps * c_in, NT = (filters + 15) / 16, hop = stride * c_in;

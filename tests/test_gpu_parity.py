@@ -677,9 +677,11 @@ def test_conv1d_reference_shape(sep, oracle):
     (2, 2500, 7, 5, 33, 2, "same", None),
     (4, 1200, 8, 4, 134, 2, "same", "relu"),         # 128 + 6 tail columns: the 8 x 8 micro-tile kernel with REM = 8
 ])
-def test_conv1d_weights_resident_kernel(sep, oracle, batch, rows, c_in, taps, filters, stride, padding, act):
-    """Calls with >= 4096 output rows and a small contraction take conv1d_rows_kernel (weights resident in shared
-    memory, 128-row tiles); every output against the oracle, and against the generic 64 x 64 kernel on a slice."""
+def test_conv1d_weights_resident_kernel(sep, oracle, monkeypatch, batch, rows, c_in, taps, filters, stride, padding, act):
+    """Calls with >= 4096 output rows and a small contraction: the reference layer (K = 80) runs on the tensor cores
+    (conv1d_tc_kernel, 3xTF32), other shapes -- and every shape with SEPCORE_CONV_SIMT=1 -- on the exact-fp32
+    weights-resident SIMT kernels; every output against the oracle, the two paths against each other, and against
+    the generic 64 x 64 kernel on a slice."""
     rng = np.random.default_rng(rows + filters)
     x = (0.3 * rng.standard_normal((batch, rows, c_in))).astype(np.float32)
     w = (0.2 * rng.standard_normal((taps, c_in, filters))).astype(np.float32)
@@ -687,6 +689,10 @@ def test_conv1d_weights_resident_kernel(sep, oracle, batch, rows, c_in, taps, fi
     got = sep.conv1d(x, w, bias, stride=stride, padding=padding, activation=act)
     want = oracle.conv1d(x, w, bias, stride=stride, padding=padding, activation=act)
     assert got.shape == want.shape and np.max(np.abs(got - want)) < 2e-5
+    monkeypatch.setenv("SEPCORE_CONV_SIMT", "1")
+    simt = sep.conv1d(x, w, bias, stride=stride, padding=padding, activation=act)
+    monkeypatch.delenv("SEPCORE_CONV_SIMT")
+    assert np.max(np.abs(simt - want)) < 2e-5 and np.max(np.abs(simt - got)) < 1e-5
     small = sep.conv1d(x[:1, :300], w, bias, stride=stride, padding=padding, activation=act)     # generic kernel
     keep = small.shape[1] - taps                      # rows whose receptive field lies inside the slice
     assert np.max(np.abs(small[0, :keep] - got[0, :keep])) < 1e-5
