@@ -651,6 +651,33 @@ def test_cfg1_hann_est_vs_ref_scoring(sep, oracle, wsj0):
         assert int(res["si_perm"][0]) == p and abs(float(res["si_best"][0]) - float(v)) < TOL_DB
 
 
+def test_fused_pit_error_distribution_cfg2(sep, oracle):
+    """The fused kernel forms the PSA labels in fp32 from its own spectra, so its PIT sums are not the fp64 sums of
+    the oracle.  Measured, not assumed: all 64 utterances of a full cfg2 batch (64 x 4 s, Blackman 256/128, ragged
+    frame_lengths) and of the Hann 256/64 variant against the oracle -- the relative error of every pair sum and
+    loss.  The contract in the other fused tests is 1e-4; what the kernel delivers is recorded here (and in
+    DESIGN.md 3): the worst value must stay below 2e-5, the median below 2e-6."""
+    import torch
+    for key in ("blackman_256_128", "hann_256_64"):
+        cfg = CONFIGS[key]
+        rng = np.random.default_rng(5)
+        mix, refs, masks, lengths = _fused_case(rng, 64, 32000, 2, cfg, oracle, ragged=True)
+        dm, dr, dk, dl = (torch.from_numpy(a).cuda() for a in (mix, refs, masks, lengths))
+        res = sep.separate_and_score(dm, dk, dr, frame_lengths=dl, **cfg)
+        pair = res["pit_pair"].cpu().numpy()
+        loss = res["pit_loss"].cpu().numpy()
+        perm = res["pit_perm"].cpu().numpy()
+        errs = []
+        for b in range(64):
+            want = oracle.separate_and_score(mix[b], refs[b], masks[b], length=lengths[b], **cfg)["pit"]
+            assert int(perm[b]) == int(want["idx"][0])
+            errs.append(np.max(np.abs(pair[b] - want["pair"][0]) / np.abs(want["pair"][0])))
+            errs.append(abs(loss[b] - want["loss"]) / abs(want["loss"]))
+        errs = np.asarray(errs)
+        print("fused PIT relative error, %s: median %.2e, 95%% %.2e, max %.2e" % (key, np.median(errs), np.quantile(errs, 0.95), errs.max()))
+        assert errs.max() < 2e-5 and np.median(errs) < 2e-6, (key, errs.max(), np.median(errs))
+
+
 # ----------------------------------------------------------------- a14 conv1d filterbank
 def test_conv1d_reference_shape(sep, oracle):
     """Raw_with_Convlayer: [B, K, 40] -> Conv1D(129, 2, sigmoid, 'same') (10449 params)."""
