@@ -67,15 +67,7 @@ struct FbArgs {
   float *est, *code;
   int64_t n, est_len;
   int n_src, frames, tiles, batch;
-  int backoff_ns;      // waits of the non-consumer roles sleep this long between polls (0: spin)
 };
-
-// A waiting role that spins on try_wait takes issue slots from the consumer warps of its scheduler; with a back-off the
-// poll costs a few instructions per sleep period.
-__device__ __forceinline__ void mbar_wait_role(uint32_t bar, uint32_t parity, int ns) {
-  if (ns <= 0) { mbar_wait(bar, parity); return; }
-  while (!mbar_try(bar, parity)) __nanosleep(ns);
-}
 
 __device__ __forceinline__ void wg_sync(int wg) {       // named barrier of one warpgroup
   asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
@@ -175,8 +167,8 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
       uint32_t round = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++round) {
         if (mt == 0) {
-          mbar_wait_role(SEP_BAR(kBarA1), round & 1, a.backoff_ns);          // frames staged
-          if (round > 0) mbar_wait_role(SEP_BAR(kBarD1Free), (round - 1) & 1, a.backoff_ns);   // D1 of the last tile drained
+          mbar_wait(SEP_BAR(kBarA1), round & 1);                             // frames staged
+          if (round > 0) mbar_wait(SEP_BAR(kBarD1Free), (round - 1) & 1);      // D1 of the last tile drained
           tc_fence_after();
           constexpr uint32_t idesc = umma_idesc_tf32(kFbM, kFbN);
           uint32_t acc = 0;
@@ -196,7 +188,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
         // D2 buffer of this tile: read by the epilogue of the tile that used it last
         const uint32_t nbuf = C <= 2 ? 2 : 1, dbuf = round % nbuf, uses = round / nbuf;
         if (uses > 0) {
-          mbar_wait_role(SEP_BAR(kBarD2Free + dbuf), (uses - 1) & 1, a.backoff_ns);
+          mbar_wait(SEP_BAR(kBarD2Free + dbuf), (uses - 1) & 1);
           tc_fence_after();
         }
         uint32_t touched = 0;                             // sources whose accumulator D2_c has been started
@@ -219,7 +211,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
             const uint32_t dcol = d2base + 2 * kFbL * c;
 #pragma unroll
             for (uint32_t h = 0; h < 2; ++h) {
-              mbar_wait_role(SEP_BAR(kBarA2Ready + 2 * w + h), (served[w] >> 1) & 1, a.backoff_ns >> 2);
+              mbar_wait(SEP_BAR(kBarA2Ready + 2 * w + h), (served[w] >> 1) & 1);
               tc_fence_after();
               // issuing threads never share an accumulator, and one thread's MMAs run in issue order:
               // D2_c[:, 0:16] += A_hi * B_hi + A_lo * B_hi,  D2_c[:, 16:32] += A_hi * B_lo
@@ -251,7 +243,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
         int j = w / C, c = w - j * C;
         for (int g = w; g < G; g += kFbWG) {
           const uint32_t slot = pf % kFbStages, nfill = pf / kFbStages;
-          if (nfill > 0) mbar_wait_role(SEP_BAR(kBarEmpty + w * kFbStages + slot), (nfill - 1) & 1, a.backoff_ns);
+          if (nfill > 0) mbar_wait(SEP_BAR(kBarEmpty + w * kFbStages + slot), (nfill - 1) & 1);
           const uint32_t full = SEP_BAR(kBarFull + w * kFbStages + slot);
           mbar_expect_tx(full, kMaskTile);
           tma_load_2d(sm0 + kOffWG + w * kWGBytes + slot * kMaskTile, &mask_map, j * kFbChunk,
@@ -287,7 +279,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
     if (blockIdx.x < n_tiles) stage_frames(blockIdx.x);
     uint32_t round = 0;
     for (int t = blockIdx.x; t + static_cast<int>(gridDim.x) < n_tiles; t += gridDim.x, ++round) {
-      mbar_wait_role(SEP_BAR(kBarG1), round & 1, a.backoff_ns);   // GEMM 1 of this tile has consumed A1
+      mbar_wait(SEP_BAR(kBarG1), round & 1);               // GEMM 1 of this tile has consumed A1
       stage_frames(t + gridDim.x);
     }
   } else {
@@ -501,10 +493,6 @@ extern "C" int sep_filterbank_separate_f32(const float *wave, const float *enc, 
               "sep_filterbank_separate_f32: wave, est and code must be 16-byte aligned");
   a.n = n_samples;
   a.est_len = est_len;
-  {
-    const char *bo = getenv("SEPCORE_FB_BACKOFF_NS");
-    a.backoff_ns = bo ? atoi(bo) : 0;
-  }
   a.n_src = n_src;
   a.batch = batch;
   a.frames = static_cast<int>(K);

@@ -4,7 +4,7 @@ inputs and against the committed golden vectors.
 
 Tolerances (BASELINE.json north_star): selected permutation bit-exact; spectra
 and waveforms within 1e-4 relative (fp32 vs the fp64 oracle; relative to the
-array scale); SI-SDR / SDR within 0.01 dB; PIT loss 1e-5 relative.
+array scale); SI-SDR / SDR within 0.01 dB; PIT loss 1e-5 relative (also inside the fused kernels: measured 6.6e-8).
 """
 import numpy as np
 import pytest
@@ -358,8 +358,8 @@ def test_fused_matches_oracle(sep, oracle, key, n_src, n):
         assert rel_l2(res["est"][b], want["ests"][:, :n]) < 1e-5
         pit = want["pit"]
         assert int(res["pit_perm"][b]) == int(pit["idx"][0])            # bit-exact permutation
-        assert np.allclose(res["pit_pair"][b], pit["pair"][0], rtol=1e-4)
-        assert abs(res["pit_loss"][b] - pit["loss"]) < 1e-4 * abs(pit["loss"])
+        assert np.allclose(res["pit_pair"][b], pit["pair"][0], rtol=TOL_LOSS)
+        assert abs(res["pit_loss"][b] - pit["loss"]) < TOL_LOSS * abs(pit["loss"])
         assert np.max(np.abs(res["si_pair"][b] - want["si_sdr_pair"])) < TOL_DB
     assert abs(res["sums"][0] - res["pit_loss"].sum()) < 1e-9 * abs(res["sums"][0])
     assert res["sums"][3] == 3
@@ -392,7 +392,7 @@ def test_fused_strip_edges(sep, oracle, key, n_src, n, batch):
         assert rel_l2(res["est"][b], want["ests"][:, :n]) < 1e-5
         pit = want["pit"]
         assert int(res["pit_perm"][b]) == int(pit["idx"][0])
-        assert np.allclose(res["pit_pair"][b], pit["pair"][0], rtol=1e-4)
+        assert np.allclose(res["pit_pair"][b], pit["pair"][0], rtol=TOL_LOSS)
         nv = int(valid[b])
         est32 = want["ests"][:, :nv].astype(np.float32)
         si = np.array([[oracle.si_sdr(refs[b, j, :nv], est32[i]) for j in range(n_src)] for i in range(n_src)])
@@ -402,7 +402,7 @@ def test_fused_strip_edges(sep, oracle, key, n_src, n, batch):
     mix2[:, : n // 3] = 0.0
     res2 = sep.separate_and_score(mix2, masks, refs, frame_lengths=lengths, **cfg)
     want2 = oracle.separate_and_score(mix2[0], refs[0], masks[0], length=lengths[0], **cfg)
-    assert np.allclose(res2["pit_pair"][0], want2["pit"]["pair"][0], rtol=1e-4)
+    assert np.allclose(res2["pit_pair"][0], want2["pit"]["pair"][0], rtol=TOL_LOSS)
     assert int(res2["pit_perm"][0]) == int(want2["pit"]["idx"][0])
 
 
@@ -430,7 +430,7 @@ def test_fused_two_strip_kernels_agree(sep, oracle, monkeypatch, key, n, batch):
     for res in (new, old):
         assert rel_err(res["est"][0], want["ests"][:, :n]) < TOL_REL
         assert int(res["pit_perm"][0]) == int(want["pit"]["idx"][0])
-        assert np.allclose(res["pit_pair"][0], want["pit"]["pair"][0], rtol=1e-4)
+        assert np.allclose(res["pit_pair"][0], want["pit"]["pair"][0], rtol=TOL_LOSS)
 
 
 def test_fused_many_short_utterances(sep, oracle, monkeypatch):
@@ -446,7 +446,7 @@ def test_fused_many_short_utterances(sep, oracle, monkeypatch):
         want = oracle.separate_and_score(mix[b], refs[b], masks[b], length=lengths[b], **cfg)
         assert rel_err(res["est"][b], want["ests"][:, :n]) < TOL_REL
         assert int(res["pit_perm"][b]) == int(want["pit"]["idx"][0])
-        assert np.allclose(res["pit_pair"][b], want["pit"]["pair"][0], rtol=1e-4)
+        assert np.allclose(res["pit_pair"][b], want["pit"]["pair"][0], rtol=TOL_LOSS)
         assert np.max(np.abs(res["si_pair"][b] - want["si_sdr_pair"])) < TOL_DB
     monkeypatch.setenv("SEPCORE_FORCE_HALFWARP", "1")
     old = sep.separate_and_score(mix, masks, refs, frame_lengths=lengths, **cfg)
@@ -491,7 +491,7 @@ def test_fused_device_tensors_full_size(sep, oracle, key):
         want = oracle.separate_and_score(mix[b], refs[b], masks[b], **cfg)
         assert rel_err(est[b], want["ests"][:, :32000]) < TOL_REL
         assert int(res["pit_perm"][b].item()) == int(want["pit"]["idx"][0])
-        assert abs(res["pit_loss"][b].item() - want["pit"]["loss"]) < 1e-4 * abs(want["pit"]["loss"])
+        assert abs(res["pit_loss"][b].item() - want["pit"]["loss"]) < TOL_LOSS * abs(want["pit"]["loss"])
         assert np.max(np.abs(res["si_pair"][b].cpu().numpy() - want["si_sdr_pair"])) < TOL_DB
     # host-pointer mode gives the same numbers, bit for bit, as device-pointer mode on the same call
     # (the strip partition -- which frames share a complex transform -- depends on the batch
@@ -523,8 +523,8 @@ def test_fused_cfg4_full_size(sep, oracle):
         assert rel_l2(est[b], want["ests"][:, :n]) < 1e-5
         pit = want["pit"]
         assert int(res["pit_perm"][b].item()) == int(pit["idx"][0])          # one of 6 permutations, exact
-        assert np.allclose(res["pit_costs"][b].cpu().numpy(), pit["costs"][0], rtol=1e-4)
-        assert abs(res["pit_loss"][b].item() - pit["loss"]) < 1e-4 * abs(pit["loss"])
+        assert np.allclose(res["pit_costs"][b].cpu().numpy(), pit["costs"][0], rtol=TOL_LOSS)
+        assert abs(res["pit_loss"][b].item() - pit["loss"]) < TOL_LOSS * abs(pit["loss"])
         assert np.max(np.abs(res["si_pair"][b].cpu().numpy() - want["si_sdr_pair"])) < TOL_DB
     # linearity over the whole batch: masks that sum to one -> the three estimates sum to the mixture
     comp = dk.clone()
@@ -655,8 +655,9 @@ def test_fused_pit_error_distribution_cfg2(sep, oracle):
     """The fused kernel forms the PSA labels in fp32 from its own spectra, so its PIT sums are not the fp64 sums of
     the oracle.  Measured, not assumed: all 64 utterances of a full cfg2 batch (64 x 4 s, Blackman 256/128, ragged
     frame_lengths) and of the Hann 256/64 variant against the oracle -- the relative error of every pair sum and
-    loss.  The contract in the other fused tests is 1e-4; what the kernel delivers is recorded here (and in
-    DESIGN.md 3): the worst value must stay below 2e-5, the median below 2e-6."""
+    loss.  Measured on B200: median 5.7e-8, maximum 6.6e-8 for both parameterisations, so every fused test uses the
+    1e-5 contract of the unfused kernel (round 1 allowed 1e-4 here); this test keeps a tighter watch: worst value
+    below 1e-6."""
     import torch
     for key in ("blackman_256_128", "hann_256_64"):
         cfg = CONFIGS[key]
@@ -675,7 +676,7 @@ def test_fused_pit_error_distribution_cfg2(sep, oracle):
             errs.append(abs(loss[b] - want["loss"]) / abs(want["loss"]))
         errs = np.asarray(errs)
         print("fused PIT relative error, %s: median %.2e, 95%% %.2e, max %.2e" % (key, np.median(errs), np.quantile(errs, 0.95), errs.max()))
-        assert errs.max() < 2e-5 and np.median(errs) < 2e-6, (key, errs.max(), np.median(errs))
+        assert errs.max() < 1e-6, (key, errs.max(), np.median(errs))
 
 
 # ----------------------------------------------------------------- a14 conv1d filterbank
