@@ -774,6 +774,34 @@ def test_host_pipeline_and_graph_match_sync_call(sep, oracle):
             assert np.array_equal(g.sums[i + 3].cpu().numpy(), want[i]["sums"])
 
 
+@pytest.mark.parametrize("key,n_src,n", [("blackman_256_128", 2, 8000), ("hann_512_128", 3, 9000),
+                                         ("blackman_256_128", 3, 6000), ("hamming_128_32", 2, 3000),
+                                         ("blackman_256_128", 1, 5000)])
+def test_push_sums_single_rank(sep, oracle, key, n_src, n):
+    """sep_fused_separate_push_f32 with a one-rank world: every fused kernel family (whole-warp 256 / 512 strips,
+    half-warp strips, tile kernel, generic kernel + separate sums kernel) writes its batch sums into the inbox slot it
+    was given, bumps that slot's arrival counter once, leaves the other slots alone -- and returns the same results as
+    the call without a push."""
+    import torch
+    from sepcore import distributed as d
+    cfg = CONFIGS[key]
+    rng = np.random.default_rng(n + n_src)
+    mix, refs, masks, _ = _fused_case(rng, 4, n, n_src, cfg, oracle)
+    dm, dr, dk = (torch.from_numpy(a).cuda() for a in (mix, refs, masks))
+    plain = sep.separate_and_score(dm, dk, dr, **cfg)
+    peer = d.PeerSums(slots=3)
+    try:
+        for rep in range(2):
+            res = sep.separate_and_score(dm, dk, dr, push=peer.target(1), **cfg)
+        torch.cuda.synchronize()
+        assert torch.equal(res["scores"], plain["scores"]) and torch.equal(res["sums"], plain["sums"])
+        assert torch.equal(peer.reduced()[1], plain["sums"])
+        assert peer.arrived.cpu().tolist() == [0, 2, 0]
+        assert float(peer.rows[[0, 2]].abs().sum().item()) == 0.0
+    finally:
+        peer.close()
+
+
 def test_single_launch_finalisation_matches(sep, oracle, monkeypatch):
     """By default the finalisation is folded into the fused kernel (the last strip of an utterance
     finalises it); SEPCORE_SINGLE_LAUNCH=0 runs it as separate kernels: same arithmetic, bit-identical
