@@ -22,6 +22,7 @@
 // 101 KB for the reference layer) stay in shared memory for the lifetime of the CTA.  Waiting roles back off with
 // nanosleep: a spinning mbarrier loop on 5 warps was taking issue slots from the epilogue (ncu, first version).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "umma.cuh"
@@ -222,8 +223,311 @@ __global__ void __launch_bounds__(kCtThreads, 1) conv1d_tc_kernel(const ConvTcAr
 #undef CT_BAR
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// conv1d_tc2_kernel -- the same contraction with the OUTPUT TILE AS ONE BULK STORE (odd `filters`, e.g. the
+// reference's 129).  Rows are numbered across the whole [batch * rows_out] output, so a 128-row tile is one
+// contiguous run of 128 * filters floats in HBM:
+//   * the A operand (the tile's im2col rows, hi | lo) lives in TENSOR MEMORY (lane = row; the staging thread that owns
+//     a row writes it with tcgen05.st), which frees the shared memory for two output tiles;
+//   * the epilogue thread of a row applies the activation and stores its values into a shared-memory image of the
+//     output tile (pitch = filters floats, odd, so the 32 rows of a warp hit 32 different banks); when the two warps of
+//     a 32-row quarter are done, one thread hands the quarter (32 * filters * 4 bytes, contiguous in HBM) to the TMA
+//     engine (cp.async.bulk shared -> global).  No transposes, no per-element global stores, no LDS in the epilogue;
+//   * the bias is folded into the activation's first FFMA (sigmoid: ex2(d * -log2e - bias * log2e)).
+//   * the accumulator is ONE buffer split into two column groups [0, split) | [split, NP), each with its own MMAs
+//     (N = 64 and 80 here), its own full / empty barriers and its own epilogue warpgroup: while one group's warps run
+//     their activations the tensor pipe refills the other group's columns; the A operand is double buffered, so the
+//     staging of tile i + 1 overlaps the MMAs of tile i.
+// TMEM columns: D [0, NP), A buffer h at NP + 2 K h: hi K columns | lo K columns  (464 of 512 here).
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// the registers pass THROUGH the wait, so no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void bulk_store(void *gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
+}
+__device__ __forceinline__ void pair_sync(int quarter) {      // the two epilogue warps of a 32-row quarter
+  asm volatile("bar.sync %0, 64;" :: "r"(1 + quarter) : "memory");
+}
+
+enum : int { kC2AFull = 0, kC2AEmpty = 2, kC2DFull = 4, kC2DEmpty = 6 };   // two of each
+
+template <int KQ, int ACT>
+__global__ void __launch_bounds__(kCtThreads, 1) conv1d_tc2_kernel(const ConvTcArgs a) {
+  static_assert(KQ % 2 == 0, "the staging threads write 8 columns of tensor memory at a time");
+  extern __shared__ __align__(128) unsigned char sm[];
+  constexpr int K = 4 * KQ;
+  const int NP = a.npad, bbytes = KQ * (NP / 8) * 128;             // one B operand
+  const int tile_bytes = kCtM * a.filters * 4, qbytes = 32 * a.filters * 4;
+  unsigned char *Bhi = sm, *Blo = sm + bbytes, *ob = Blo + bbytes; // two output tiles behind the weights
+  float *nb = reinterpret_cast<float *>(ob + 2 * tile_bytes);      // per column: the bias term of the activation
+  uint64_t *bars = reinterpret_cast<uint64_t *>(nb + NP);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+  const uint32_t bar0 = smem_u32(bars), sm0 = smem_u32(sm);
+#define CT_BAR(i) (bar0 + 8u * static_cast<uint32_t>(i))
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t total_rows = static_cast<int64_t>(a.batch) * a.rows_out;
+  const int n_tiles = static_cast<int>((total_rows + kCtM - 1) / kCtM);
+  const uint32_t lbo_b = (NP / 8) * 128;
+  const int split = (NP / 32) * 16;                                // columns [0, split) | [split, NP): the two epilogue groups
+  constexpr float kLog2e = 1.4426950408889634f;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (threadIdx.x == 0) {
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(CT_BAR(kC2AFull + h), 128);
+      mbar_init(CT_BAR(kC2AEmpty + h), 1);
+      mbar_init(CT_BAR(kC2DFull + h), 1);
+      mbar_init(CT_BAR(kC2DEmpty + h), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // weights W [K][filters] row-major -> B[n][k] (N rows, K-major), split hi / lo; columns beyond `filters` are zero
+  for (int e = threadIdx.x; e < K * NP; e += kCtThreads) {
+    const int k = e / NP, n = e - k * NP;
+    float hi = 0.f, lo = 0.f;
+    if (n < a.filters) split_tf32(__ldg(a.w + static_cast<int64_t>(k) * a.filters + n), hi, lo);
+    const int o = kmajor_off(n, k, NP / 8);
+    *reinterpret_cast<float *>(Bhi + o) = hi;
+    *reinterpret_cast<float *>(Blo + o) = lo;
+  }
+  for (int n = threadIdx.x; n < NP; n += kCtThreads) {
+    const float bv = (a.bias && n < a.filters) ? __ldg(a.bias + n) : 0.f;
+    nb[n] = ACT == SEP_ACT_SIGMOID ? -kLog2e * bv : bv;
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tm_a = tmem + NP;                                 // A buffer h at + 2 K h: hi K columns, lo K columns
+
+  if (warp == 12) {
+    // =========================== MMA warp: one thread issues ===========================
+    if (lane == 0) {
+      const uint32_t idesc[2] = {umma_idesc_tf32(kCtM, split), umma_idesc_tf32(kCtM, NP - split)};
+      uint32_t i = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+        const uint32_t abuf = i & 1;
+        mbar_wait(CT_BAR(kC2AFull + abuf), (i >> 1) & 1);            // the tile's rows are in tensor memory
+        const uint32_t ta = tm_a + 2 * K * abuf;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {                                // the two column groups: own accumulator, own epilogue
+          if (i > 0) mbar_wait(CT_BAR(kC2DEmpty + g), (i - 1) & 1);  // group g has drained the previous tile
+          tc_fence_after();
+          const uint32_t d = tmem + g * split, boff = sm0 + g * (split / 8) * 128;
+#pragma unroll
+          for (int ks = 0; ks < K / 8; ++ks) {                       // hi*hi, lo*hi, hi*lo per 8-wide k-step
+            const uint64_t bhi = umma_desc(boff + ks * 2 * lbo_b, lbo_b, 128);
+            const uint64_t blo = umma_desc(boff + bbytes + ks * 2 * lbo_b, lbo_b, 128);
+            umma_tf32_ts(d, ta + 8 * ks, bhi, idesc[g], ks > 0 ? 1u : 0u);
+            umma_tf32_ts(d, ta + K + 8 * ks, bhi, idesc[g], 1u);
+            umma_tf32_ts(d, ta + 8 * ks, blo, idesc[g], 1u);
+          }
+          umma_commit(CT_BAR(kC2DFull + g));                         // this group's accumulator is complete
+        }
+        umma_commit(CT_BAR(kC2AEmpty + abuf));                       // the A columns may be overwritten
+      }
+    }
+  } else if (warp >= 8) {
+    // =========================== staging warps: thread s = row s of the tile = TMEM lane s ===========================
+    const int s = threadIdx.x - 256;
+    const int64_t n_x = static_cast<int64_t>(a.rows) * a.c_in;
+    const int hop = a.stride * a.c_in;
+    const uint32_t a_addr = tm_a + (static_cast<uint32_t>(s & ~31) << 16);
+    float4 pre[KQ];
+    auto row_of = [&](int t, const float *&xb, int64_t &g0) -> bool {
+      const int64_t R = static_cast<int64_t>(t) * kCtM + s;
+      const int64_t b = R / a.rows_out;
+      const int ro = static_cast<int>(R - b * a.rows_out);
+      xb = a.x + b * n_x;
+      g0 = static_cast<int64_t>(ro) * hop - static_cast<int64_t>(a.left) * a.c_in;
+      return R < total_rows;
+    };
+    auto fetch = [&](int t) {
+      const float *xb;
+      int64_t g0;
+      const bool live = row_of(t, xb, g0);
+      if (live && g0 >= 0 && g0 + K <= n_x && ((reinterpret_cast<uintptr_t>(xb + g0) & 15) == 0)) {
+#pragma unroll
+        for (int q = 0; q < KQ; ++q) pre[q] = __ldg(reinterpret_cast<const float4 *>(xb + g0) + q);
+      } else {
+#pragma unroll
+        for (int q = 0; q < KQ; ++q) {
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int64_t g = g0 + 4 * q + e;
+            v[e] = (live && g >= 0 && g < n_x) ? __ldg(xb + g) : 0.f;   // 'same' padding / beyond the last row
+          }
+          pre[q] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+    };
+    auto prefetch_l2 = [&](int t) {                                  // the rows of a later tile: on their way into L2
+      const float *xb;
+      int64_t g0;
+      if (t < n_tiles && row_of(t, xb, g0) && g0 >= 0 && g0 + K <= n_x) {
+        const char *p = reinterpret_cast<const char *>(xb + g0);
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(p + 4 * K - 4));
+      }
+    };
+    if (blockIdx.x < n_tiles) fetch(blockIdx.x);
+    prefetch_l2(blockIdx.x + gridDim.x);
+    uint32_t i = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+      const uint32_t abuf = i & 1;
+      if (i > 1) {
+        mbar_wait(CT_BAR(kC2AEmpty + abuf), ((i >> 1) - 1) & 1);     // the MMAs two tiles back have read this A buffer
+        tc_fence_after();
+      }
+      __syncwarp();                                                  // tcgen05.st is warp-collective
+      const uint32_t ta = a_addr + 2 * K * abuf;
+#pragma unroll
+      for (int g = 0; g < KQ / 2; ++g) {
+        float hi[8], lo[8];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const float4 v = pre[2 * g + q];
+          split_tf32(v.x, hi[4 * q], lo[4 * q]); split_tf32(v.y, hi[4 * q + 1], lo[4 * q + 1]);
+          split_tf32(v.z, hi[4 * q + 2], lo[4 * q + 2]); split_tf32(v.w, hi[4 * q + 3], lo[4 * q + 3]);
+        }
+        tmem_st8(ta + 8 * g, hi);
+        tmem_st8(ta + K + 8 * g, lo);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(CT_BAR(kC2AFull + abuf));
+      if (t + static_cast<int>(gridDim.x) < n_tiles) fetch(t + gridDim.x);   // the next tile's rows (L2 hits, prefetched a tile ago)
+      prefetch_l2(t + 2 * gridDim.x);
+    }
+  } else {
+    // =========================== epilogue warps: TMEM lane = row ===========================
+    // warps w (columns [0, split)) and w + 4 (columns [split, NP)) share TMEM lanes 32 (w & 3) ..
+    const int quarter = warp & 3, grp = warp >> 2;
+    const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    const bool issuer = grp == 0 && lane == 0;
+    const int pair_tid = grp * 32 + lane;
+    const int cbeg = grp ? split : 0, cend = grp ? NP : split;
+    uint32_t i = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+      unsigned char *otile = ob + (i & 1) * tile_bytes;
+      float *orow = reinterpret_cast<float *>(otile) + (quarter * 32 + lane) * a.filters;
+      if (issuer) bulk_wait_read<1>();                               // the store of tile i - 2 has read this buffer
+      pair_sync(quarter);
+      mbar_wait(CT_BAR(kC2DFull + grp), i & 1);
+      tc_fence_after();
+      uint32_t r0[16], r1[16];
+      const uint32_t dcol = lane_addr + cbeg;
+      const int n_chunks = (cend - cbeg) >> 4;
+      // 16 columns of this row: straight-line code (16 independent FFMA -> EX2 -> FADD -> RCP -> STS chains keep the
+      // MUFU pipe fed from one warp); only a chunk that straddles `filters` takes the predicated path
+      auto finish_chunk = [&](const uint32_t (&r)[16], int c0) {
+        const float4 *nb4 = reinterpret_cast<const float4 *>(nb + c0);
+        float bb[16], v[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 bq = nb4[q];
+          bb[4 * q] = bq.x; bb[4 * q + 1] = bq.y; bb[4 * q + 2] = bq.z; bb[4 * q + 3] = bq.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float d = __uint_as_float(r[e]);
+          if (ACT == SEP_ACT_SIGMOID) v[e] = rcp_approx(1.f + ex2_approx(fmaf(d, -kLog2e, bb[e])));
+          else if (ACT == SEP_ACT_RELU) v[e] = fmaxf(d + bb[e], 0.f);
+          else v[e] = d + bb[e];
+        }
+        const int live = a.filters - c0;
+        if (live >= 16) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) orow[c0 + e] = v[e];
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (e < live) orow[c0 + e] = v[e];
+        }
+      };
+      auto drained = [&]() {                                         // this thread's last read of the accumulator is done
+        tc_fence_before();
+        mbar_arrive(CT_BAR(kC2DEmpty + grp));
+      };
+      tmem_ld16_issue(dcol, r0);
+      tmem_ld16_wait(r0);
+#pragma unroll 1
+      for (int it = 0; it < n_chunks; it += 2) {                     // two chunks per trip: the register sets alternate
+        const int c0 = cbeg + 16 * it;
+        const bool second = it + 1 < n_chunks, third = it + 2 < n_chunks;
+        if (second) tmem_ld16_issue(dcol + 16 * (it + 1), r1);       // in flight during the activations
+        else drained();
+        finish_chunk(r0, c0);
+        if (second) {
+          tmem_ld16_wait(r1);
+          if (third) tmem_ld16_issue(dcol + 16 * (it + 2), r0);
+          else drained();
+          finish_chunk(r1, c0 + 16);
+          if (third) tmem_ld16_wait(r0);
+        }
+      }
+      fence_async_smem();                                            // this thread's tile values -> visible to the TMA engine
+      pair_sync(quarter);
+      const int64_t R0 = static_cast<int64_t>(t) * kCtM + quarter * 32;
+      const int rows_here = static_cast<int>(std::min<int64_t>(32, total_rows - R0));
+      if (rows_here > 0) {
+        float *gdst = a.out + R0 * a.filters;
+        const uint32_t bytes = static_cast<uint32_t>(rows_here) * a.filters * 4u;
+        if ((bytes & 15u) == 0) {
+          if (issuer) bulk_store(gdst, smem_u32(otile + quarter * qbytes), bytes);
+        } else {                                                     // a ragged last quarter: plain stores
+          const float *src = reinterpret_cast<const float *>(otile + quarter * qbytes);
+          for (int e = pair_tid; e < rows_here * a.filters; e += 64) gdst[e] = src[e];
+        }
+      }
+    }
+    if (issuer) bulk_wait_read<0>();                                 // shared memory stays valid until the engine has read it
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u));
+  }
+#undef CT_BAR
+}
+
 // Takes the call when the shape fits; *handled tells.  Needs K = taps * c_in == 80 (the reference layer; other
-// contractions stay on the SIMT kernels), filters <= 256, and enough rows to fill the machine.
+// contractions stay on the SIMT kernels), filters <= 256, and enough rows to fill the machine.  Odd filter counts
+// (the reference's 129) run on conv1d_tc2_kernel (bulk-stored output tiles); SEPCORE_CONV_TC1=1 keeps the first kernel.
 int conv1d_tc_try(const float *d_x, const float *d_w, const float *d_b, int batch, int rows, int c_in, int taps,
                   int filters, int stride, int left, int rows_out, int act, float *d_out, cudaStream_t stream,
                   bool *handled) {
@@ -231,15 +535,36 @@ int conv1d_tc_try(const float *d_x, const float *d_w, const float *d_b, int batc
   constexpr int KQ = 20;
   const int K = taps * c_in, NP = (filters + 15) / 16 * 16;
   if (K != 4 * KQ || NP > 256 || static_cast<int64_t>(batch) * rows_out < 4096) return SEP_OK;
+  ConvTcArgs a{d_x, d_w, d_b, d_out, batch, rows, c_in, taps, filters, stride, left, rows_out, act, NP};
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const char *v1_env = getenv("SEPCORE_CONV_TC1");
+  const bool v1_only = v1_env && atoi(v1_env) != 0;
+  const size_t smem2 = 2 * static_cast<size_t>(KQ) * (NP / 8) * 128 + 2 * static_cast<size_t>(kCtM) * filters * 4 +
+                       static_cast<size_t>(NP) * 4 + 128;
+  if (!v1_only && (filters & 1) && NP >= 32 && NP + 4 * K <= 512 && smem2 <= 227 * 1024 &&
+      (reinterpret_cast<uintptr_t>(d_out) & 15) == 0) {
+    *handled = true;
+    void (*kern)(ConvTcArgs) = act == SEP_ACT_SIGMOID ? conv1d_tc2_kernel<KQ, SEP_ACT_SIGMOID>
+                               : act == SEP_ACT_RELU  ? conv1d_tc2_kernel<KQ, SEP_ACT_RELU>
+                                                      : conv1d_tc2_kernel<KQ, SEP_ACT_LINEAR>;
+    SEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
+    const int64_t tiles = (static_cast<int64_t>(batch) * rows_out + kCtM - 1) / kCtM;
+    const int grid = static_cast<int>(std::min<int64_t>(tiles, sms));
+    profile_begin(stream, "conv1d_tc2_kernel<K=%d> (tcgen05 kind::tf32 x3, A in TMEM x2, M=128 N=%d+%d, output tiles by "
+                  "cp.async.bulk; taps=%d c_in=%d filters=%d stride=%d)", K, (NP / 32) * 16, NP - (NP / 32) * 16, taps, c_in,
+                  filters, stride);
+    kern<<<grid, kCtThreads, smem2, stream>>>(a);
+    profile_end(stream);
+    SEP_LAUNCHED();
+    return SEP_OK;
+  }
   const size_t smem = 2 * static_cast<size_t>(KQ + 2) * (kCtM / 8) * 128 + 2 * static_cast<size_t>(KQ + 2) * (NP / 8) * 128 +
                       8 * 32 * 17 * sizeof(float) + 128;
   if (smem > 225 * 1024) return SEP_OK;
   *handled = true;
-  ConvTcArgs a{d_x, d_w, d_b, d_out, batch, rows, c_in, taps, filters, stride, left, rows_out, act, NP};
   SEP_CUDA(cudaFuncSetAttribute(conv1d_tc_kernel<KQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t tiles = static_cast<int64_t>(batch) * ((rows_out + kCtM - 1) / kCtM);
   const int grid = static_cast<int>(std::min<int64_t>(tiles, sms));
   profile_begin(stream, "conv1d_tc_kernel<K=%d> (tcgen05 kind::tf32 x3, M=128 N=%d, TMEM accumulators x2; taps=%d c_in=%d "

@@ -700,7 +700,10 @@ def test_conv1d_reference_shape(sep, oracle):
 
 @pytest.mark.parametrize("batch,rows,c_in,taps,filters,stride,padding,act", [
     (8, 800, 40, 2, 129, 1, "same", "sigmoid"),      # the reference layer on 4 s utterances: weights-resident kernel
-    (5, 1001, 40, 2, 129, 1, "same", "sigmoid"),     # rows not a multiple of the 128-row tile
+    (5, 1001, 40, 2, 129, 1, "same", "sigmoid"),     # rows not a multiple of the 128-row tile (ragged last quarter)
+    (7, 1002, 40, 2, 129, 1, "same", "relu"),        # 7014 rows: the last tile ends inside a quarter, 16-byte multiple
+    (6, 900, 40, 2, 64, 1, "same", "sigmoid"),       # even filter count: the first tcgen05 kernel (transposing epilogue)
+    (4, 2100, 20, 4, 131, 2, "valid", None),         # K = 80 from 4 taps x 20 channels, stride 2, no activation
     (3, 4000, 1, 16, 64, 8, "valid", "relu"),        # strided frames (an encoder-shaped call), 4 columns per thread
     (2, 2500, 7, 5, 33, 2, "same", None),
     (4, 1200, 8, 4, 134, 2, "same", "relu"),         # 128 + 6 tail columns: the 8 x 8 micro-tile kernel with REM = 8
@@ -721,6 +724,10 @@ def test_conv1d_weights_resident_kernel(sep, oracle, monkeypatch, batch, rows, c
     simt = sep.conv1d(x, w, bias, stride=stride, padding=padding, activation=act)
     monkeypatch.delenv("SEPCORE_CONV_SIMT")
     assert np.max(np.abs(simt - want)) < 2e-5 and np.max(np.abs(simt - got)) < 1e-5
+    monkeypatch.setenv("SEPCORE_CONV_TC1", "1")      # the two tcgen05 kernels against each other
+    tc1 = sep.conv1d(x, w, bias, stride=stride, padding=padding, activation=act)
+    monkeypatch.delenv("SEPCORE_CONV_TC1")
+    assert np.max(np.abs(tc1 - want)) < 2e-5 and np.max(np.abs(tc1 - got)) < 1e-5
     small = sep.conv1d(x[:1, :300], w, bias, stride=stride, padding=padding, activation=act)     # generic kernel
     keep = small.shape[1] - taps                      # rows whose receptive field lies inside the slice
     assert np.max(np.abs(small[0, :keep] - got[0, :keep])) < 1e-5
