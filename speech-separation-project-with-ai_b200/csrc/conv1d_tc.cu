@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include "umma.cuh"
 
+
 namespace sep {
 
 constexpr int kCtM = 128;                         // rows per tile (MMA M)
@@ -233,13 +234,19 @@ __global__ void __launch_bounds__(kCtThreads, 1) conv1d_tc_kernel(const ConvTcAr
 //   * the epilogue thread of a row applies the activation and stores its values into a shared-memory image of the
 //     output tile (pitch = filters floats, odd, so the 32 rows of a warp hit 32 different banks); when the two warps of
 //     a 32-row quarter are done, one thread hands the quarter (32 * filters * 4 bytes, contiguous in HBM) to the TMA
-//     engine (cp.async.bulk shared -> global).  No transposes, no per-element global stores, no LDS in the epilogue;
-//   * the bias is folded into the activation's first FFMA (sigmoid: ex2(d * -log2e - bias * log2e)).
-//   * the accumulator is ONE buffer split into two column groups [0, split) | [split, NP), each with its own MMAs
-//     (N = 64 and 80 here), its own full / empty barriers and its own epilogue warpgroup: while one group's warps run
-//     their activations the tensor pipe refills the other group's columns; the A operand is double buffered, so the
-//     staging of tile i + 1 overlaps the MMAs of tile i.
-// TMEM columns: D [0, NP), A buffer h at NP + 2 K h: hi K columns | lo K columns  (464 of 512 here).
+//     engine (cp.async.bulk shared -> global).  No transposes, no per-element global stores;
+//   * the bias is folded into the activation's first FFMA (sigmoid: ex2(d * -log2e - bias * log2e));
+//   * hand-offs: the A operand is handed over per K half (own full / empty barriers: the staging of the next tile's
+//     first half overlaps the MMAs on the second half), the accumulator is double buffered, a store warp issues the
+//     bulk stores so that no epilogue warp waits for another one, and every wait is a hardware-suspending try_wait.
+// Roles: warps 0-7 epilogue (two per 32-row quarter: columns [0, split) | [split, filters)), 8-11 staging, 12 MMA
+// issue (converged warp, one elected lane), 13 bulk stores.
+// TMEM columns: D0 [0, NP), D1 [NP, 2 NP), A_hi [2 NP, 2 NP + K), A_lo [2 NP + K, 2 NP + 2 K)  (448 of 512 here).
+// What bounds it (in-kernel clock64 timelines and one-role-removed builds, round 2): the tensor-memory READ port.  An
+// MMA whose A operand sits in tensor memory reads its 128 x 8 words at 64 B per cycle -- 64 cycles whatever N is (so
+// two N / 2 column groups cost twice one N-wide MMA: tried, slower) -- and the epilogue's tcgen05.ld goes through the
+// same port; MMAs and the epilogue of the previous tile slow each other down to ~5500 cycles per tile against 2400
+// (MMA floor) and 2300 (MUFU floor of the sigmoids: 2 x 8 cycles per warp instruction, measured) when run alone.
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -255,41 +262,103 @@ __device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
                  "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
                :: "memory");
 }
-__device__ __forceinline__ float ex2_approx(float x) {
+__device__ __forceinline__ float ex2_pinned(float x) {
   float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float rcp_approx(float x) {
+__device__ __forceinline__ float rcp_pinned(float x) {
   float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// v[e] = act(d[e] + bias[e]) for N values; bb holds the bias (sigmoid: -log2e * bias)
+template <int ACT, int N>
+__device__ __forceinline__ void activate16(const uint32_t (&r)[16], const float (&bb)[16], float (&v)[16]) {
+  constexpr float kLog2e = 1.4426950408889634f;
+  if (ACT == SEP_ACT_SIGMOID) {
+#pragma unroll
+    for (int e = 0; e < N; ++e) v[e] = fmaf(__uint_as_float(r[e]), -kLog2e, bb[e]);
+#pragma unroll
+    for (int e = 0; e < N; ++e) v[e] = ex2_pinned(v[e]);
+#pragma unroll
+    for (int e = 0; e < N; ++e) v[e] = 1.f + v[e];
+#pragma unroll
+    for (int e = 0; e < N; ++e) v[e] = rcp_pinned(v[e]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < N; ++e) {
+      const float d = __uint_as_float(r[e]) + bb[e];
+      v[e] = ACT == SEP_ACT_RELU ? fmaxf(d, 0.f) : d;
+    }
+  }
+}
+__device__ __forceinline__ void tmem_ld4_issue(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld4_wait(uint32_t (&r)[4]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) :: "memory");
+}
+template <int ACT>
+__device__ __forceinline__ void activate4(const uint32_t (&r)[4], const float (&bb)[4], float (&v)[4]) {
+  constexpr float kLog2e = 1.4426950408889634f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float d = __uint_as_float(r[e]);
+    if (ACT == SEP_ACT_SIGMOID) v[e] = rcp_pinned(1.f + ex2_pinned(fmaf(d, -kLog2e, bb[e])));
+    else if (ACT == SEP_ACT_RELU) v[e] = fmaxf(d + bb[e], 0.f);
+    else v[e] = d + bb[e];
+  }
 }
 __device__ __forceinline__ void bulk_store(void *gdst, uint32_t ssrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
 }
-__device__ __forceinline__ void pair_sync(int quarter) {      // the two epilogue warps of a 32-row quarter
-  asm volatile("bar.sync %0, 64;" :: "r"(1 + quarter) : "memory");
+// the issuing warp runs CONVERGED and one elected lane executes the instruction: descriptors and addresses are then
+// warp-uniform values the compiler keeps in uniform registers, instead of moving them there (R2UR) in front of every MMA
+__device__ __forceinline__ void umma_tf32_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
+      :: "r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
-
-enum : int { kC2AFull = 0, kC2AEmpty = 2, kC2DFull = 4, kC2DEmpty = 6 };   // two of each
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" :: "r"(bar) : "memory");
+}
+// mbarrier wait that SUSPENDS the warp in hardware (try_wait with a suspend-time hint) instead of polling: the waiting
+// roles share their scheduler with the epilogue warps, and a polling loop takes the issue slots the epilogue needs
+__device__ __forceinline__ void mbar_wait_suspend(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP_S:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra WAIT_DONE_S;\n\t"
+      "bra WAIT_LOOP_S;\n\t"
+      "WAIT_DONE_S:\n\t}\n"
+      :: "r"(bar), "r"(parity), "r"(20000u) : "memory");
+}
+enum : int { kC2AFull = 0, kC2AEmpty = 2, kC2DFull = 4, kC2DEmpty = 6, kC2OEmpty = 8, kC2OFull = 10, kC2Bars = 18 };
+constexpr int kCt2Threads = kCtThreads + 32;       // + the store warp
 
 template <int KQ, int ACT>
-__global__ void __launch_bounds__(kCtThreads, 1) conv1d_tc2_kernel(const ConvTcArgs a) {
-  static_assert(KQ % 2 == 0, "the staging threads write 8 columns of tensor memory at a time");
+__global__ void __launch_bounds__(kCt2Threads, 1) conv1d_tc2_kernel(const ConvTcArgs a) {
+  static_assert(KQ % 4 == 0, "the staging threads write 8 columns of tensor memory at a time, per K half");
   extern __shared__ __align__(128) unsigned char sm[];
   constexpr int K = 4 * KQ;
   const int NP = a.npad, bbytes = KQ * (NP / 8) * 128;             // one B operand
   const int tile_bytes = kCtM * a.filters * 4, qbytes = 32 * a.filters * 4;
   unsigned char *Bhi = sm, *Blo = sm + bbytes, *ob = Blo + bbytes; // two output tiles behind the weights
   float *nb = reinterpret_cast<float *>(ob + 2 * tile_bytes);      // per column: the bias term of the activation
-  uint64_t *bars = reinterpret_cast<uint64_t *>(nb + NP);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(nb + NP + 32);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + kC2Bars);
   const uint32_t bar0 = smem_u32(bars), sm0 = smem_u32(sm);
 #define CT_BAR(i) (bar0 + 8u * static_cast<uint32_t>(i))
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -308,12 +377,14 @@ __global__ void __launch_bounds__(kCtThreads, 1) conv1d_tc2_kernel(const ConvTcA
       mbar_init(CT_BAR(kC2AFull + h), 128);
       mbar_init(CT_BAR(kC2AEmpty + h), 1);
       mbar_init(CT_BAR(kC2DFull + h), 1);
-      mbar_init(CT_BAR(kC2DEmpty + h), 128);
+      mbar_init(CT_BAR(kC2DEmpty + h), 256);
+      mbar_init(CT_BAR(kC2OEmpty + h), 1);
+      for (int q = 0; q < 4; ++q) mbar_init(CT_BAR(kC2OFull + 2 * q + h), 64);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // weights W [K][filters] row-major -> B[n][k] (N rows, K-major), split hi / lo; columns beyond `filters` are zero
-  for (int e = threadIdx.x; e < K * NP; e += kCtThreads) {
+  for (int e = threadIdx.x; e < K * NP; e += kCt2Threads) {
     const int k = e / NP, n = e - k * NP;
     float hi = 0.f, lo = 0.f;
     if (n < a.filters) split_tf32(__ldg(a.w + static_cast<int64_t>(k) * a.filters + n), hi, lo);
@@ -321,7 +392,7 @@ __global__ void __launch_bounds__(kCtThreads, 1) conv1d_tc2_kernel(const ConvTcA
     *reinterpret_cast<float *>(Bhi + o) = hi;
     *reinterpret_cast<float *>(Blo + o) = lo;
   }
-  for (int n = threadIdx.x; n < NP; n += kCtThreads) {
+  for (int n = threadIdx.x; n < NP + 32; n += kCt2Threads) {
     const float bv = (a.bias && n < a.filters) ? __ldg(a.bias + n) : 0.f;
     nb[n] = ACT == SEP_ACT_SIGMOID ? -kLog2e * bv : bv;
   }
@@ -330,36 +401,60 @@ __global__ void __launch_bounds__(kCtThreads, 1) conv1d_tc2_kernel(const ConvTcA
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tm_a = tmem + NP;                                 // A buffer h at + 2 K h: hi K columns, lo K columns
+  const uint32_t tm_a = tmem + 2 * NP;                             // A: hi K columns | lo K columns
 
-  if (warp == 12) {
-    // =========================== MMA warp: one thread issues ===========================
+  if (warp == 13) {
+    // =========================== store warp: one thread hands finished quarters to the TMA engine ===========================
     if (lane == 0) {
-      const uint32_t idesc[2] = {umma_idesc_tf32(kCtM, split), umma_idesc_tf32(kCtM, NP - split)};
       uint32_t i = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
-        const uint32_t abuf = i & 1;
-        mbar_wait(CT_BAR(kC2AFull + abuf), (i >> 1) & 1);            // the tile's rows are in tensor memory
-        const uint32_t ta = tm_a + 2 * K * abuf;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {                                // the two column groups: own accumulator, own epilogue
-          if (i > 0) mbar_wait(CT_BAR(kC2DEmpty + g), (i - 1) & 1);  // group g has drained the previous tile
-          tc_fence_after();
-          const uint32_t d = tmem + g * split, boff = sm0 + g * (split / 8) * 128;
-#pragma unroll
-          for (int ks = 0; ks < K / 8; ++ks) {                       // hi*hi, lo*hi, hi*lo per 8-wide k-step
-            const uint64_t bhi = umma_desc(boff + ks * 2 * lbo_b, lbo_b, 128);
-            const uint64_t blo = umma_desc(boff + bbytes + ks * 2 * lbo_b, lbo_b, 128);
-            umma_tf32_ts(d, ta + 8 * ks, bhi, idesc[g], ks > 0 ? 1u : 0u);
-            umma_tf32_ts(d, ta + K + 8 * ks, bhi, idesc[g], 1u);
-            umma_tf32_ts(d, ta + 8 * ks, blo, idesc[g], 1u);
-          }
-          umma_commit(CT_BAR(kC2DFull + g));                         // this group's accumulator is complete
+        if (i > 0) {
+          bulk_wait_read<0>();                                       // the engine has read the previous tile's buffer:
+          mbar_arrive(CT_BAR(kC2OEmpty + ((i - 1) & 1)));            // the epilogue may write it again
         }
-        umma_commit(CT_BAR(kC2AEmpty + abuf));                       // the A columns may be overwritten
+        unsigned char *otile = ob + (i & 1) * tile_bytes;
+        for (int q = 0; q < 4; ++q) {
+          mbar_wait_suspend(CT_BAR(kC2OFull + 2 * q + (i & 1)), (i >> 1) & 1);   // both column groups have written these 32 rows
+          const int64_t R0 = static_cast<int64_t>(t) * kCtM + q * 32;
+          const int rows_here = static_cast<int>(std::min<int64_t>(32, total_rows - R0));
+          const uint32_t bytes = static_cast<uint32_t>(rows_here > 0 ? rows_here : 0) * a.filters * 4u;
+          if (bytes > 0 && (bytes & 15u) == 0)                       // (a ragged last quarter is stored by its writers)
+            bulk_store(a.out + R0 * a.filters, smem_u32(otile + q * qbytes), bytes);
+        }
+        bulk_commit();
+      }
+      bulk_wait_read<0>();                                           // shared memory stays valid until the engine has read it
+    }
+  } else if (warp == 12) {
+    // =========================== MMA warp: runs converged, one elected lane issues ===========================
+    // ONE accumulator of N = NP columns: with the A operand in tensor memory an MMA costs max(N / 2, 64) cycles (the
+    // 4 KB of A are read at the 64 B per cycle of the tensor-memory read port), so two N / 2 halves cost twice as much
+    {
+      const uint32_t idesc = umma_idesc_tf32(kCtM, NP);
+      uint32_t i = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+        const uint32_t dbuf = i & 1;
+        if (i > 1) mbar_wait_suspend(CT_BAR(kC2DEmpty + dbuf), ((i >> 1) - 1) & 1);   // the epilogue has drained this accumulator
+        const uint32_t d = tmem + dbuf * NP;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                                // the two K halves of A: own full / empty barriers
+          mbar_wait_suspend(CT_BAR(kC2AFull + h), i & 1);            // this half of the tile's rows is in tensor memory
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < K / 16; ++kk) {                      // hi*hi, lo*hi, hi*lo per 8-wide k-step
+            const int ks = h * (K / 16) + kk;
+            const uint64_t bhi = umma_desc(sm0 + ks * 2 * lbo_b, lbo_b, 128);
+            const uint64_t blo = umma_desc(sm0 + bbytes + ks * 2 * lbo_b, lbo_b, 128);
+            umma_tf32_ts_elect(d, tm_a + 8 * ks, bhi, idesc, ks > 0 ? 1u : 0u);
+            umma_tf32_ts_elect(d, tm_a + K + 8 * ks, bhi, idesc, 1u);
+            umma_tf32_ts_elect(d, tm_a + 8 * ks, blo, idesc, 1u);
+          }
+          umma_commit_elect(CT_BAR(kC2AEmpty + h));                  // this half of A may be overwritten
+        }
+        umma_commit_elect(CT_BAR(kC2DFull + dbuf));                  // the accumulator is complete
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 12) {
     // =========================== staging warps: thread s = row s of the tile = TMEM lane s ===========================
     const int s = threadIdx.x - 256;
     const int64_t n_x = static_cast<int64_t>(a.rows) * a.c_in;
@@ -407,28 +502,30 @@ __global__ void __launch_bounds__(kCtThreads, 1) conv1d_tc2_kernel(const ConvTcA
     prefetch_l2(blockIdx.x + gridDim.x);
     uint32_t i = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
-      const uint32_t abuf = i & 1;
-      if (i > 1) {
-        mbar_wait(CT_BAR(kC2AEmpty + abuf), ((i >> 1) - 1) & 1);     // the MMAs two tiles back have read this A buffer
-        tc_fence_after();
-      }
-      __syncwarp();                                                  // tcgen05.st is warp-collective
-      const uint32_t ta = a_addr + 2 * K * abuf;
 #pragma unroll
-      for (int g = 0; g < KQ / 2; ++g) {
-        float hi[8], lo[8];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const float4 v = pre[2 * g + q];
-          split_tf32(v.x, hi[4 * q], lo[4 * q]); split_tf32(v.y, hi[4 * q + 1], lo[4 * q + 1]);
-          split_tf32(v.z, hi[4 * q + 2], lo[4 * q + 2]); split_tf32(v.w, hi[4 * q + 3], lo[4 * q + 3]);
+      for (int h = 0; h < 2; ++h) {
+        if (i > 0) {
+          mbar_wait_suspend(CT_BAR(kC2AEmpty + h), (i - 1) & 1);             // the previous tile's MMAs have read this half of A
+          tc_fence_after();
         }
-        tmem_st8(ta + 8 * g, hi);
-        tmem_st8(ta + K + 8 * g, lo);
+        __syncwarp();                                                // tcgen05.st is warp-collective
+#pragma unroll
+        for (int gg = 0; gg < KQ / 4; ++gg) {
+          const int g = h * (KQ / 4) + gg;
+          float hi[8], lo[8];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const float4 v = pre[2 * g + q];
+            split_tf32(v.x, hi[4 * q], lo[4 * q]); split_tf32(v.y, hi[4 * q + 1], lo[4 * q + 1]);
+            split_tf32(v.z, hi[4 * q + 2], lo[4 * q + 2]); split_tf32(v.w, hi[4 * q + 3], lo[4 * q + 3]);
+          }
+          tmem_st8(a_addr + 8 * g, hi);
+          tmem_st8(a_addr + K + 8 * g, lo);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(CT_BAR(kC2AFull + h));
       }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(CT_BAR(kC2AFull + abuf));
       if (t + static_cast<int>(gridDim.x) < n_tiles) fetch(t + gridDim.x);   // the next tile's rows (L2 hits, prefetched a tile ago)
       prefetch_l2(t + 2 * gridDim.x);
     }
@@ -437,23 +534,26 @@ __global__ void __launch_bounds__(kCtThreads, 1) conv1d_tc2_kernel(const ConvTcA
     // warps w (columns [0, split)) and w + 4 (columns [split, NP)) share TMEM lanes 32 (w & 3) ..
     const int quarter = warp & 3, grp = warp >> 2;
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
-    const bool issuer = grp == 0 && lane == 0;
-    const int pair_tid = grp * 32 + lane;
     const int cbeg = grp ? split : 0, cend = grp ? NP : split;
     uint32_t i = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
       unsigned char *otile = ob + (i & 1) * tile_bytes;
       float *orow = reinterpret_cast<float *>(otile) + (quarter * 32 + lane) * a.filters;
-      if (issuer) bulk_wait_read<1>();                               // the store of tile i - 2 has read this buffer
-      pair_sync(quarter);
-      mbar_wait(CT_BAR(kC2DFull + grp), i & 1);
+      if (i > 1) mbar_wait_suspend(CT_BAR(kC2OEmpty + (i & 1)), ((i >> 1) - 1) & 1);   // the store of tile i - 2 has read this buffer
+      mbar_wait_suspend(CT_BAR(kC2DFull + (i & 1)), (i >> 1) & 1);
       tc_fence_after();
-      uint32_t r0[16], r1[16];
-      const uint32_t dcol = lane_addr + cbeg;
-      const int n_chunks = (cend - cbeg) >> 4;
-      // 16 columns of this row: straight-line code (16 independent FFMA -> EX2 -> FADD -> RCP -> STS chains keep the
-      // MUFU pipe fed from one warp); only a chunk that straddles `filters` takes the predicated path
-      auto finish_chunk = [&](const uint32_t (&r)[16], int c0) {
+      uint32_t r0[16], r1[16], rx[4];
+      const uint32_t dcol = lane_addr + (i & 1) * NP + cbeg;
+      // chunks of 16 columns that exist in full, then `rem` more columns; up to 4 of those (the reference's 129th
+      // column) ride with the last full chunk instead of costing a chunk of their own
+      const int cols = min(cend, a.filters) - cbeg, full = cols >> 4, rem = cols & 15;
+      const bool ride = rem > 0 && rem <= 4 && full > 0;
+      const int n_chunks = full + ((rem > 0 && !ride) ? 1 : 0);
+      // 16 columns of this row.  The order of the special-function instructions is PINNED (asm volatile): 16 x EX2, then
+      // 16 x RCP.  Left to itself ptxas puts each dependent FADD / RCP two instructions behind its EX2, and with two
+      // epilogue warps per scheduler nothing hides the 20-cycle MUFU latency.
+      auto finish_chunk = [&](const uint32_t (&r)[16], int ch) {
+        const int c0 = cbeg + 16 * ch;
         const float4 *nb4 = reinterpret_cast<const float4 *>(nb + c0);
         float bb[16], v[16];
 #pragma unroll
@@ -461,60 +561,64 @@ __global__ void __launch_bounds__(kCtThreads, 1) conv1d_tc2_kernel(const ConvTcA
           const float4 bq = nb4[q];
           bb[4 * q] = bq.x; bb[4 * q + 1] = bq.y; bb[4 * q + 2] = bq.z; bb[4 * q + 3] = bq.w;
         }
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float d = __uint_as_float(r[e]);
-          if (ACT == SEP_ACT_SIGMOID) v[e] = rcp_approx(1.f + ex2_approx(fmaf(d, -kLog2e, bb[e])));
-          else if (ACT == SEP_ACT_RELU) v[e] = fmaxf(d + bb[e], 0.f);
-          else v[e] = d + bb[e];
-        }
-        const int live = a.filters - c0;
-        if (live >= 16) {
+        activate16<ACT, 16>(r, bb, v);
+        if (ch < full) {
 #pragma unroll
           for (int e = 0; e < 16; ++e) orow[c0 + e] = v[e];
+          if (ride && ch == full - 1) {                              // + the columns that ride along
+            const float4 bq = nb4[4];
+            const float bx[4] = {bq.x, bq.y, bq.z, bq.w};
+            float vx[4];
+            activate4<ACT>(rx, bx, vx);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (e < rem) orow[c0 + 16 + e] = vx[e];
+          }
         } else {
 #pragma unroll
           for (int e = 0; e < 16; ++e)
-            if (e < live) orow[c0 + e] = v[e];
+            if (e < rem) orow[c0 + e] = v[e];
         }
       };
       auto drained = [&]() {                                         // this thread's last read of the accumulator is done
         tc_fence_before();
-        mbar_arrive(CT_BAR(kC2DEmpty + grp));
+        mbar_arrive(CT_BAR(kC2DEmpty + (i & 1)));
       };
-      tmem_ld16_issue(dcol, r0);
-      tmem_ld16_wait(r0);
+      auto load_chunk = [&](int ch, uint32_t (&r)[16]) {
+        tmem_ld16_issue(dcol + 16 * ch, r);
+        if (ride && ch == full - 1) tmem_ld4_issue(dcol + 16 * full, rx);
+      };
+      auto wait_chunk = [&](int ch, uint32_t (&r)[16]) {
+        tmem_ld16_wait(r);
+        if (ride && ch == full - 1) tmem_ld4_wait(rx);
+      };
+      load_chunk(0, r0);
+      wait_chunk(0, r0);
 #pragma unroll 1
       for (int it = 0; it < n_chunks; it += 2) {                     // two chunks per trip: the register sets alternate
-        const int c0 = cbeg + 16 * it;
         const bool second = it + 1 < n_chunks, third = it + 2 < n_chunks;
-        if (second) tmem_ld16_issue(dcol + 16 * (it + 1), r1);       // in flight during the activations
+        if (second) load_chunk(it + 1, r1);                          // in flight during the activations
         else drained();
-        finish_chunk(r0, c0);
+        finish_chunk(r0, it);
         if (second) {
-          tmem_ld16_wait(r1);
-          if (third) tmem_ld16_issue(dcol + 16 * (it + 2), r0);
+          wait_chunk(it + 1, r1);
+          if (third) load_chunk(it + 2, r0);
           else drained();
-          finish_chunk(r1, c0 + 16);
-          if (third) tmem_ld16_wait(r0);
+          finish_chunk(r1, it + 1);
+          if (third) wait_chunk(it + 2, r0);
         }
       }
-      fence_async_smem();                                            // this thread's tile values -> visible to the TMA engine
-      pair_sync(quarter);
       const int64_t R0 = static_cast<int64_t>(t) * kCtM + quarter * 32;
       const int rows_here = static_cast<int>(std::min<int64_t>(32, total_rows - R0));
-      if (rows_here > 0) {
-        float *gdst = a.out + R0 * a.filters;
-        const uint32_t bytes = static_cast<uint32_t>(rows_here) * a.filters * 4u;
-        if ((bytes & 15u) == 0) {
-          if (issuer) bulk_store(gdst, smem_u32(otile + quarter * qbytes), bytes);
-        } else {                                                     // a ragged last quarter: plain stores
-          const float *src = reinterpret_cast<const float *>(otile + quarter * qbytes);
-          for (int e = pair_tid; e < rows_here * a.filters; e += 64) gdst[e] = src[e];
-        }
+      if (rows_here > 0 && ((static_cast<uint32_t>(rows_here) * a.filters * 4u) & 15u) != 0) {
+        // a ragged last quarter (its byte count is no multiple of 16): plain stores of this thread's own columns
+        float *grow = a.out + (R0 + lane) * a.filters;
+        if (lane < rows_here)
+          for (int c = cbeg; c < cend && c < a.filters; ++c) grow[c] = orow[c];
       }
+      fence_async_smem();                                            // this thread's tile values -> visible to the TMA engine
+      mbar_arrive(CT_BAR(kC2OFull + 2 * quarter + (i & 1)));
     }
-    if (issuer) bulk_wait_read<0>();                                 // shared memory stays valid until the engine has read it
   }
   tc_fence_before();
   __syncthreads();
@@ -542,8 +646,8 @@ int conv1d_tc_try(const float *d_x, const float *d_w, const float *d_b, int batc
   const char *v1_env = getenv("SEPCORE_CONV_TC1");
   const bool v1_only = v1_env && atoi(v1_env) != 0;
   const size_t smem2 = 2 * static_cast<size_t>(KQ) * (NP / 8) * 128 + 2 * static_cast<size_t>(kCtM) * filters * 4 +
-                       static_cast<size_t>(NP) * 4 + 128;
-  if (!v1_only && (filters & 1) && NP >= 32 && NP + 4 * K <= 512 && smem2 <= 227 * 1024 &&
+                       static_cast<size_t>(NP + 32) * 4 + 8 * kC2Bars + 64;
+  if (!v1_only && (filters & 1) && NP >= 32 && 2 * NP + 2 * K <= 512 && smem2 <= 227 * 1024 &&
       (reinterpret_cast<uintptr_t>(d_out) & 15) == 0) {
     *handled = true;
     void (*kern)(ConvTcArgs) = act == SEP_ACT_SIGMOID ? conv1d_tc2_kernel<KQ, SEP_ACT_SIGMOID>
@@ -555,7 +659,7 @@ int conv1d_tc_try(const float *d_x, const float *d_w, const float *d_b, int batc
     profile_begin(stream, "conv1d_tc2_kernel<K=%d> (tcgen05 kind::tf32 x3, A in TMEM x2, M=128 N=%d+%d, output tiles by "
                   "cp.async.bulk; taps=%d c_in=%d filters=%d stride=%d)", K, (NP / 32) * 16, NP - (NP / 32) * 16, taps, c_in,
                   filters, stride);
-    kern<<<grid, kCtThreads, smem2, stream>>>(a);
+    kern<<<grid, kCt2Threads, smem2, stream>>>(a);
     profile_end(stream);
     SEP_LAUNCHED();
     return SEP_OK;
