@@ -233,6 +233,22 @@ def test_pit_mse(sep, oracle, n_src, feat):
     assert loss.dtype == np.float32 and abs(loss - want["loss"]) < 1e-5 * abs(want["loss"])
 
 
+
+@pytest.mark.parametrize("case", ["small", "cfg", "tie"])
+def test_pit_mse_against_reference_cell(sep, case):
+    """The CUDA pit_loss against the output of the reference's own cell 28 (tests/golden/pit_golden.npz, made by
+    oracle/make_golden_pit.py): loss within 1e-5 relative, gradient within 1e-5."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pit_golden.npz"))
+    y_true, y_pred = g[case + "_y_true"].astype(np.float32), g[case + "_y_pred"].astype(np.float32)
+    feat, want = int(g[case + "_feat"]), float(g[case + "_loss"])
+    got = sep.pit_mse(y_true, y_pred, feat, with_grad=True)
+    assert abs(got["loss"] - want) < 1e-5 * abs(want)
+    assert np.allclose(got["grad"], g[case + "_grad"], rtol=1e-4, atol=1e-6)
+    loss = sep.pit_with_outputsize(feat)(y_true, y_pred)
+    assert abs(loss - want) < 1e-5 * abs(want)
+
+
 def test_pit_permutation_semantics(sep, oracle):
     rng = np.random.default_rng(7)
     y_true, y_pred = _pit_inputs(rng, 6, 30, 129, 2, [30] * 6)
