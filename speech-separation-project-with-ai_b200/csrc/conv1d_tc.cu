@@ -319,32 +319,6 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
 }
-// the issuing warp runs CONVERGED and one elected lane executes the instruction: descriptors and addresses are then
-// warp-uniform values the compiler keeps in uniform registers, instead of moving them there (R2UR) in front of every MMA
-__device__ __forceinline__ void umma_tf32_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc,
-                                                   uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
-      :: "r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
-}
-__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
-  asm volatile(
-      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
-      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" :: "r"(bar) : "memory");
-}
-// mbarrier wait that SUSPENDS the warp in hardware (try_wait with a suspend-time hint) instead of polling: the waiting
-// roles share their scheduler with the epilogue warps, and a polling loop takes the issue slots the epilogue needs
-__device__ __forceinline__ void mbar_wait_suspend(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_LOOP_S:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-      "@p bra WAIT_DONE_S;\n\t"
-      "bra WAIT_LOOP_S;\n\t"
-      "WAIT_DONE_S:\n\t}\n"
-      :: "r"(bar), "r"(parity), "r"(20000u) : "memory");
-}
 enum : int { kC2AFull = 0, kC2AEmpty = 2, kC2DFull = 4, kC2DEmpty = 6, kC2OEmpty = 8, kC2OFull = 10, kC2Bars = 18 };
 constexpr int kCt2Threads = kCtThreads + 32;       // + the store warp
 

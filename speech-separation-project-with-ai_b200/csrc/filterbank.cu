@@ -160,15 +160,15 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
   if (warp == 4 * kFbWG || warp == 4 * kFbWG + 1) {
     // =========================== MMA warps (one lane each issues) ===========================
     const int mt = warp - 4 * kFbWG;
-    if (lane == 0 && mt < n_mma) {
+    if (mt < n_mma) {                                    // the whole warp runs the loop; one elected lane issues
       uint32_t served[kFbWG];                          // items served per warpgroup, all tiles (phase of a2_ready)
 #pragma unroll
       for (int w = 0; w < kFbWG; ++w) served[w] = 0;
       uint32_t round = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++round) {
         if (mt == 0) {
-          mbar_wait(SEP_BAR(kBarA1), round & 1);                             // frames staged
-          if (round > 0) mbar_wait(SEP_BAR(kBarD1Free), (round - 1) & 1);      // D1 of the last tile drained
+          mbar_wait_suspend(SEP_BAR(kBarA1), round & 1);                             // frames staged
+          if (round > 0) mbar_wait_suspend(SEP_BAR(kBarD1Free), (round - 1) & 1);      // D1 of the last tile drained
           tc_fence_after();
           constexpr uint32_t idesc = umma_idesc_tf32(kFbM, kFbN);
           uint32_t acc = 0;
@@ -178,17 +178,17 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
             const uint32_t boff = sm0 + (pass == 2 ? kOffB1Lo : kOffB1Hi);
 #pragma unroll
             for (int ks = 0; ks < kFbL / 8; ++ks) {
-              umma_tf32(tmem, umma_desc(aoff + ks * 2 * kLboA1, kLboA1, kSbo),
+              umma_tf32_elect(tmem, umma_desc(aoff + ks * 2 * kLboA1, kLboA1, kSbo),
                         umma_desc(boff + ks * 2 * kLboB1, kLboB1, kSbo), idesc, acc);
               acc = 1;
             }
           }
-          umma_commit(SEP_BAR(kBarG1));
+          umma_commit_elect(SEP_BAR(kBarG1));
         }
         // D2 buffer of this tile: read by the epilogue of the tile that used it last
         const uint32_t nbuf = C <= 2 ? 2 : 1, dbuf = round % nbuf, uses = round / nbuf;
         if (uses > 0) {
-          mbar_wait(SEP_BAR(kBarD2Free + dbuf), (uses - 1) & 1);
+          mbar_wait_suspend(SEP_BAR(kBarD2Free + dbuf), (uses - 1) & 1);
           tc_fence_after();
         }
         uint32_t touched = 0;                             // sources whose accumulator D2_c has been started
@@ -211,15 +211,15 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
             const uint32_t dcol = d2base + 2 * kFbL * c;
 #pragma unroll
             for (uint32_t h = 0; h < 2; ++h) {
-              mbar_wait(SEP_BAR(kBarA2Ready + 2 * w + h), (served[w] >> 1) & 1);
+              mbar_wait_suspend(SEP_BAR(kBarA2Ready + 2 * w + h), (served[w] >> 1) & 1);
               tc_fence_after();
               // issuing threads never share an accumulator, and one thread's MMAs run in issue order:
               // D2_c[:, 0:16] += A_hi * B_hi + A_lo * B_hi,  D2_c[:, 16:32] += A_hi * B_lo
               const uint32_t a2 = tmem + kTmA2 + 32 * w + 16 * h;
               const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(((j * (kFbChunk / 4) + 2 * h) * kLboB2) >> 4);
-              umma_tf32_ts(dcol, a2, bdesc, idesc32, (touched >> c) & 1u);
-              umma_tf32_ts(dcol, a2 + 8, bdesc, idesc16, 1u);
-              umma_commit(SEP_BAR(kBarA2Free + 2 * w + h));
+              umma_tf32_ts_elect(dcol, a2, bdesc, idesc32, (touched >> c) & 1u);
+              umma_tf32_ts_elect(dcol, a2 + 8, bdesc, idesc16, 1u);
+              umma_commit_elect(SEP_BAR(kBarA2Free + 2 * w + h));
               touched |= 1u << c;
               ++served[w];
             }
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
             more = more || gw[w] < G;
           }
         }
-        umma_commit(SEP_BAR(kBarD2));
+        umma_commit_elect(SEP_BAR(kBarD2));
       }
     }
   } else if (warp == 4 * kFbWG + 2) {
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
         int j = w / C, c = w - j * C;
         for (int g = w; g < G; g += kFbWG) {
           const uint32_t slot = pf % kFbStages, nfill = pf / kFbStages;
-          if (nfill > 0) mbar_wait(SEP_BAR(kBarEmpty + w * kFbStages + slot), (nfill - 1) & 1);
+          if (nfill > 0) mbar_wait_suspend(SEP_BAR(kBarEmpty + w * kFbStages + slot), (nfill - 1) & 1);
           const uint32_t full = SEP_BAR(kBarFull + w * kFbStages + slot);
           mbar_expect_tx(full, kMaskTile);
           tma_load_2d(sm0 + kOffWG + w * kWGBytes + slot * kMaskTile, &mask_map, j * kFbChunk,
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
     if (blockIdx.x < n_tiles) stage_frames(blockIdx.x);
     uint32_t round = 0;
     for (int t = blockIdx.x; t + static_cast<int>(gridDim.x) < n_tiles; t += gridDim.x, ++round) {
-      mbar_wait(SEP_BAR(kBarG1), round & 1);               // GEMM 1 of this tile has consumed A1
+      mbar_wait_suspend(SEP_BAR(kBarG1), round & 1);               // GEMM 1 of this tile has consumed A1
       stage_frames(t + gridDim.x);
     }
   } else {
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
       const int frame = k0 + m;
       const bool row_ok = frame < K;
       const bool owner = row_ok && (m > 0 || tile == 0);    // row 0 of a later tile is the halo frame
-      mbar_wait(SEP_BAR(kBarG1), round & 1);
+      mbar_wait_suspend(SEP_BAR(kBarG1), round & 1);
       tc_fence_after();
 
       int j = wg / C, c = wg - j * C;                       // work item g = wg, wg + 4, ...: (j, c) kept incrementally
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
 #pragma unroll
         for (int e = 0; e < kFbChunk; ++e) d[e] = fmaxf(d[e], 0.f);
         const uint32_t slot = fills % kFbStages;
-        mbar_wait(SEP_BAR(kBarFull + wg * kFbStages + slot), (fills / kFbStages) & 1);
+        mbar_wait_suspend(SEP_BAR(kBarFull + wg * kFbStages + slot), (fills / kFbStages) & 1);
         const unsigned char *mk_s = ring + slot * kMaskTile + m * 64;
         float2 p[kFbChunk / 2];
 #pragma unroll
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           if (use > 0) {
-            mbar_wait(SEP_BAR(kBarA2Free + 2 * wg + h), (use - 1) & 1);
+            mbar_wait_suspend(SEP_BAR(kBarA2Free + 2 * wg + h), (use - 1) & 1);
             tc_fence_after();
           }
           __syncwarp();
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
 
       // ---- sum of the warpgroups' D2_c -> overlap-add of neighbouring frames -> est ----
       if (wg < C) {
-        mbar_wait(SEP_BAR(kBarD2), round & 1);
+        mbar_wait_suspend(SEP_BAR(kBarD2), round & 1);
         tc_fence_after();
       }
       for (int cc = wg; cc < C; cc += kFbWG) {
