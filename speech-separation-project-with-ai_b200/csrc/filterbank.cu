@@ -39,8 +39,8 @@ constexpr int kFbN = 256;        // filters
 constexpr int kFbL = 16;         // taps
 constexpr int kFbHop = 8;
 constexpr int kFbChunk = 16;     // code columns per decoder work item
-constexpr int kFbWG = 4;         // warpgroups per CTA; warpgroup w takes work items w, w + 4, ...
-constexpr int kFbThreads = 128 * kFbWG + 128;  // + two MMA-issue warps + a TMA warp + a frame-staging warp
+constexpr int kFbWG = 4;         // consumer warpgroups per CTA; warpgroup w works for source w mod C
+constexpr int kFbThreads = 128 * kFbWG + 32 * kFbWG + 32;  // + one MMA-issue warp per warpgroup + a frame-staging warp
 constexpr int kFbStages = 4;     // mask tiles in flight per warpgroup (TMA ring, one mbarrier pair per slot)
 
 // ---- shared memory map (bytes) ----
@@ -54,8 +54,8 @@ constexpr int kOffB1Hi = kOffA1Lo + kA1Bytes, kOffB1Lo = kOffB1Hi + kB1Bytes;
 constexpr int kOffB2Hi = kOffB1Lo + kB1Bytes, kOffB2Lo = kOffB2Hi + kB2Bytes;
 constexpr int kOffWG = kOffB2Lo + kB2Bytes;          // per warpgroup: mask ring, `up`
 constexpr int kWGBytes = kFbStages * kMaskTile + kFbM * 8 * 4;
-// tensor memory columns: D1 [0, 256); D2 [256, 384): 32 columns per source (hi*hi + lo*hi | hi*lo), two
-// tile buffers when C <= 2; masked code A2 of warpgroup w: two 8-column buffers at 384 + 32 w + 16 h (hi | lo)
+// tensor memory columns: D1 [0, 256); D2 [256, 384): 32 columns per WARPGROUP (its partial sum over its code columns:
+// hi*hi + lo*hi | hi*lo); masked code A2 of warpgroup w: two 8-column buffers at 384 + 32 w + 16 h (hi | lo)
 constexpr int kTmD2 = kFbN, kTmA2 = kFbN + 128;
 constexpr int kOffBar = kOffWG + kFbWG * kWGBytes;   // mbarriers + tmem address + has[][] table
 constexpr int kFbSmem = kOffBar + 768;
@@ -74,24 +74,27 @@ __device__ __forceinline__ void wg_sync(int wg) {       // named barrier of one 
 }
 
 // One persistent CTA per SM, warp-specialised:
-//   warpgroups 0..3 (consumers): per work item (16 code columns j of source c) of a 128-frame tile:
-//       D1 chunk -> registers (tcgen05.ld), relu, times the mask tile in shared memory, split hi / lo
-//       -> the warpgroup's A2 buffer -> arrive on `a2_ready`; then the epilogue of the tile
-//   warp 16 (MMA): GEMM 1 of every tile as soon as its frames are staged and D1 has been drained;
-//       the 6 decoder MMAs of whichever warpgroup's A2 buffer is ready, into that warpgroup's own
-//       accumulator D2[w][c]; commits free the A2 buffers / publish D1 and D2
-//   warp 17 (producer): mask tiles by TMA into per-warpgroup rings, the next tile's frames -> A1
+//   warpgroups 0..3 (consumers): warpgroup w < n_active works for source w mod C on the 16-column code chunks
+//       j = w / C, w / C + n_active / C, ...: D1 chunk -> registers (tcgen05.ld), relu, times the mask tile in shared
+//       memory, split hi / lo -> its A2 buffer -> arrive on `a2_ready`; then the epilogue of the tile
+//   warp 16 + w (MMA issue for warpgroup w; the warp runs converged, one elected lane issues): the decoder MMAs of
+//       every half item of ITS warpgroup into that warpgroup's own accumulator D2[w], and the TMA refill of the mask
+//       slot the half item came from (a2_ready of an item implies that all 128 threads have read its mask tile); warp
+//       16 also issues GEMM 1 of every tile.  tcgen05.mma costs ~60-100 issue cycles per instruction from one warp
+//       whatever its size (descriptor and address moves into uniform registers), and the decoder is 128 small MMAs per
+//       tile: four issuing warps, none waiting for another warpgroup's hand-off (round 1/2 first version: two issuers
+//       for two warpgroups each, 147.6 -> 118 us with converged issue, -> this layout)
+//   warp 20 (frame staging): the next tile's frames -> A1
 // Nobody meets at a block barrier inside the tile loop; all hand-offs are mbarriers.
 enum : int {
   kBarG1 = 0,            // GEMM 1 of the tile done (commit)
-  kBarD2 = 1,            // all decoder MMAs of the tile done (commit)
+  kBarD2 = 1,            // all decoder MMAs of the tile done (one commit per active issuer)
   kBarA1 = 2,            // frames of the tile staged (32 producer lanes)
-  kBarD1Free = 3,        // every consumer has read its last D1 chunk (512)
-  kBarD2Free = 4,        // [buffer] the epilogue has read D2 (128 per source); buffers alternate per tile when C <= 2
+  kBarD1Free = 3,        // every active consumer has read its last D1 chunk (128 n_active)
+  kBarD2Free = 4,        // the epilogue has read D2 (128 per source)
   kBarA2Ready = 48,      // [2 w + h] half h (8 code columns) of an item written to A2 buffer h (128)
   kBarA2Free = 56,       // [2 w + h] the decoder MMAs that read A2 buffer h are done (commit)
   kBarFull = 16,         // [w * stages + s] mask tile landed (TMA transaction)
-  kBarEmpty = 32,        // [w * stages + s] mask tile read by the whole warpgroup (128)
 };
 
 __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs a,
@@ -104,7 +107,9 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + kOffBar + 640);
   const uint32_t bar0 = smem_u32(bars), sm0 = smem_u32(sm);
 #define SEP_BAR(i) (bar0 + 8u * static_cast<uint32_t>(i))
-  const int G = (kFbN / kFbChunk) * C;
+  // warpgroups at work: the largest multiple of C that fits (C = 3: three); each serves ONE source
+  const int n_active = C >= kFbWG ? kFbWG : (kFbWG / C) * C, per_src = n_active / (C < kFbWG ? C : kFbWG);
+  const int n_items = (kFbN / kFbChunk) / per_src;          // 16-column chunks per warpgroup and tile
   const int n_tiles = a.tiles * a.batch;
 
   if (threadIdx.x < 32) {
@@ -113,20 +118,16 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
   }
   if (threadIdx.x == 0) {
     mbar_init(SEP_BAR(kBarG1), 1);
-    mbar_init(SEP_BAR(kBarD2), (C == 2 || C == 4) ? 2 : 1);
+    mbar_init(SEP_BAR(kBarD2), n_active);
     mbar_init(SEP_BAR(kBarA1), 32);
-    mbar_init(SEP_BAR(kBarD1Free), 128 * kFbWG);
+    mbar_init(SEP_BAR(kBarD1Free), 128 * n_active);
     mbar_init(SEP_BAR(kBarD2Free), 128 * (C < kFbWG ? C : kFbWG));
-    mbar_init(SEP_BAR(kBarD2Free + 1), 128 * (C < kFbWG ? C : kFbWG));
     for (int w = 0; w < kFbWG; ++w) {
       for (int h = 0; h < 2; ++h) {
         mbar_init(SEP_BAR(kBarA2Ready + 2 * w + h), 128);
         mbar_init(SEP_BAR(kBarA2Free + 2 * w + h), 1);
       }
-      for (int st = 0; st < kFbStages; ++st) {
-        mbar_init(SEP_BAR(kBarFull + w * kFbStages + st), 1);
-        mbar_init(SEP_BAR(kBarEmpty + w * kFbStages + st), 128);
-      }
+      for (int st = 0; st < kFbStages; ++st) mbar_init(SEP_BAR(kBarFull + w * kFbStages + st), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -154,19 +155,33 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  // With C = 2 or 4 a warpgroup always feeds the same source (w mod C), so two issuing threads can split the
-  // warpgroups {0, 2} / {1, 3} without ever sharing an accumulator; otherwise one thread issues everything.
-  const int n_mma = (C == 2 || C == 4) ? 2 : 1;
-  if (warp == 4 * kFbWG || warp == 4 * kFbWG + 1) {
-    // =========================== MMA warps (one lane each issues) ===========================
-    const int mt = warp - 4 * kFbWG;
-    if (mt < n_mma) {                                    // the whole warp runs the loop; one elected lane issues
-      uint32_t served[kFbWG];                          // items served per warpgroup, all tiles (phase of a2_ready)
-#pragma unroll
-      for (int w = 0; w < kFbWG; ++w) served[w] = 0;
+  if (warp >= 4 * kFbWG && warp < 5 * kFbWG) {
+    // =========================== MMA warps (converged; one elected lane issues) ===========================
+    const int w = warp - 4 * kFbWG;                        // the warpgroup this warp issues for
+    if (w < n_active || w == 0) {
+      const int c = w % C, j0 = w / C;                     // its source, its first chunk
+      uint32_t served = 0;                                 // half items served, all tiles (phase of a2_ready)
+      uint32_t pf = 0;                                     // mask tiles requested, all tiles
+      int pf_t = blockIdx.x, pf_i = 0;                     // the next mask tile to request: tile, item
+      auto request = [&]() {                               // one lane: arm the slot's barrier, start the TMA
+        if (pf_t < n_tiles) {
+          if (lane == 0) {
+            const int b = pf_t / a.tiles, k0 = (pf_t - b * a.tiles) * (kFbM - 1);
+            const uint32_t full = SEP_BAR(kBarFull + w * kFbStages + pf % kFbStages);
+            mbar_expect_tx(full, kMaskTile);
+            tma_load_2d(sm0 + kOffWG + w * kWGBytes + (pf % kFbStages) * kMaskTile, &mask_map,
+                        (j0 + pf_i * per_src) * kFbChunk, (b * C + c) * K + k0, full);
+          }
+          __syncwarp();
+          ++pf;
+          if (++pf_i == n_items) { pf_i = 0; pf_t += gridDim.x; }
+        }
+      };
+      if (w < n_active)
+        for (int st = 0; st < kFbStages; ++st) request();
       uint32_t round = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++round) {
-        if (mt == 0) {
+        if (w == 0) {
           mbar_wait_suspend(SEP_BAR(kBarA1), round & 1);                             // frames staged
           if (round > 0) mbar_wait_suspend(SEP_BAR(kBarD1Free), (round - 1) & 1);      // D1 of the last tile drained
           tc_fence_after();
@@ -179,82 +194,43 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
 #pragma unroll
             for (int ks = 0; ks < kFbL / 8; ++ks) {
               umma_tf32_elect(tmem, umma_desc(aoff + ks * 2 * kLboA1, kLboA1, kSbo),
-                        umma_desc(boff + ks * 2 * kLboB1, kLboB1, kSbo), idesc, acc);
+                              umma_desc(boff + ks * 2 * kLboB1, kLboB1, kSbo), idesc, acc);
               acc = 1;
             }
           }
           umma_commit_elect(SEP_BAR(kBarG1));
         }
-        // D2 buffer of this tile: read by the epilogue of the tile that used it last
-        const uint32_t nbuf = C <= 2 ? 2 : 1, dbuf = round % nbuf, uses = round / nbuf;
-        if (uses > 0) {
-          mbar_wait_suspend(SEP_BAR(kBarD2Free + dbuf), (uses - 1) & 1);
+        if (w >= n_active) continue;
+        // this warpgroup's accumulator: read by the epilogue of the previous tile
+        if (round > 0) {
+          mbar_wait_suspend(SEP_BAR(kBarD2Free), (round - 1) & 1);
           tc_fence_after();
         }
-        uint32_t touched = 0;                             // sources whose accumulator D2_c has been started
-        int gw[kFbWG], jw[kFbWG], cw[kFbWG];              // next work item of each warpgroup: g and its (j, c)
-#pragma unroll
-        for (int w = 0; w < kFbWG; ++w) { gw[w] = w; jw[w] = w / C; cw[w] = w - jw[w] * C; }
         constexpr uint32_t idesc32 = umma_idesc_tf32(kFbM, 2 * kFbL), idesc16 = umma_idesc_tf32(kFbM, kFbL);
         const uint64_t bdesc0 = umma_desc(sm0 + kOffB2Hi, kLboB2, kSbo);
-        const uint32_t d2base = tmem + kTmD2 + 2 * kFbL * (dbuf * C);
-        // strict round-robin over this thread's warpgroups, item by item, half by half: the consumers advance
-        // in step, so a blocking wait on the next hand-off in that order almost never waits, and no failed
-        // polls of other warpgroups' barriers sit between two services
-        bool more = true;
-        while (more) {
-          more = false;
+        const uint32_t dcol = tmem + kTmD2 + 2 * kFbL * w;
+        for (int i = 0; i < n_items; ++i) {
+          const int j = j0 + i * per_src;
 #pragma unroll
-          for (int w = 0; w < kFbWG; ++w) {
-            if (w % n_mma != mt || gw[w] >= G) continue;
-            const int j = jw[w], c = cw[w];
-            const uint32_t dcol = d2base + 2 * kFbL * c;
-#pragma unroll
-            for (uint32_t h = 0; h < 2; ++h) {
-              mbar_wait_suspend(SEP_BAR(kBarA2Ready + 2 * w + h), (served[w] >> 1) & 1);
-              tc_fence_after();
-              // issuing threads never share an accumulator, and one thread's MMAs run in issue order:
-              // D2_c[:, 0:16] += A_hi * B_hi + A_lo * B_hi,  D2_c[:, 16:32] += A_hi * B_lo
-              const uint32_t a2 = tmem + kTmA2 + 32 * w + 16 * h;
-              const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(((j * (kFbChunk / 4) + 2 * h) * kLboB2) >> 4);
-              umma_tf32_ts_elect(dcol, a2, bdesc, idesc32, (touched >> c) & 1u);
-              umma_tf32_ts_elect(dcol, a2 + 8, bdesc, idesc16, 1u);
-              umma_commit_elect(SEP_BAR(kBarA2Free + 2 * w + h));
-              touched |= 1u << c;
-              ++served[w];
-            }
-            gw[w] += kFbWG;
-            cw[w] += kFbWG;
-            while (cw[w] >= C) { cw[w] -= C; ++jw[w]; }
-            more = more || gw[w] < G;
+          for (uint32_t h = 0; h < 2; ++h) {
+            mbar_wait_suspend(SEP_BAR(kBarA2Ready + 2 * w + h), (served >> 1) & 1);
+            tc_fence_after();
+            // D2_w[:, 0:16] += A_hi * B_hi + A_lo * B_hi,  D2_w[:, 16:32] += A_hi * B_lo
+            const uint32_t a2 = tmem + kTmA2 + 32 * w + 16 * h;
+            const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(((j * (kFbChunk / 4) + 2 * h) * kLboB2) >> 4);
+            umma_tf32_ts_elect(dcol, a2, bdesc, idesc32, (i > 0 || h > 0) ? 1u : 0u);
+            umma_tf32_ts_elect(dcol, a2 + 8, bdesc, idesc16, 1u);
+            umma_commit_elect(SEP_BAR(kBarA2Free + 2 * w + h));
+            ++served;
+            // a2_ready of half 0 means that all 128 threads have used the item's mask tile (their products depend
+            // on it and were stored before they arrived): its slot takes the tile kFbStages items ahead
+            if (h == 0) request();
           }
         }
         umma_commit_elect(SEP_BAR(kBarD2));
       }
     }
-  } else if (warp == 4 * kFbWG + 2) {
-    // =========================== producer warp: mask tiles by TMA ===========================
-    // lane w feeds warpgroup w on its own: a slow warpgroup never delays the mask tiles of another one
-    if (lane < kFbWG) {
-      const int w = lane;
-      uint32_t pf = 0;                                   // mask tiles requested for this warpgroup, all tiles
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int b = t / a.tiles, k0 = (t - b * a.tiles) * (kFbM - 1);
-        int j = w / C, c = w - j * C;
-        for (int g = w; g < G; g += kFbWG) {
-          const uint32_t slot = pf % kFbStages, nfill = pf / kFbStages;
-          if (nfill > 0) mbar_wait_suspend(SEP_BAR(kBarEmpty + w * kFbStages + slot), (nfill - 1) & 1);
-          const uint32_t full = SEP_BAR(kBarFull + w * kFbStages + slot);
-          mbar_expect_tx(full, kMaskTile);
-          tma_load_2d(sm0 + kOffWG + w * kWGBytes + slot * kMaskTile, &mask_map, j * kFbChunk,
-                      (b * C + c) * K + k0, full);
-          ++pf;
-          c += kFbWG;
-          while (c >= C) { c -= C; ++j; }
-        }
-      }
-    }
-  } else if (warp == 4 * kFbWG + 3) {
+  } else if (warp == 5 * kFbWG) {
     // =========================== frame-staging warp: the next tile's frames -> A1 (hi / lo) ===========================
     auto stage_frames = [&](int t) {                     // all 32 lanes: 4 rows each
       const int b = t / a.tiles, k0 = (t - b * a.tiles) * (kFbM - 1);
@@ -302,12 +278,13 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
       mbar_wait_suspend(SEP_BAR(kBarG1), round & 1);
       tc_fence_after();
 
-      int j = wg / C, c = wg - j * C;                       // work item g = wg, wg + 4, ...: (j, c) kept incrementally
-      for (int g = wg; g < G; g += kFbWG) {
+      const int c = wg % C;                                 // this warpgroup's source
+      for (int i = 0; i < n_items && wg < n_active; ++i) {  // its chunks j = wg / C, + per_src, ...
+        const int j = wg / C + i * per_src;
         float d[kFbChunk];
         __syncwarp();                                       // tcgen05.ld is warp-collective (.sync.aligned)
         tmem_ld16(lane_addr + j * kFbChunk, d);
-        if (g + kFbWG >= G) {                               // that was this thread's last read of D1
+        if (i + 1 == n_items) {                             // that was this thread's last read of D1
           tc_fence_before();
           mbar_arrive(SEP_BAR(kBarD1Free));
         }
@@ -340,12 +317,9 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
           lo[2 * q] = l2.x;
           lo[2 * q + 1] = l2.y;
         }
-        // The producer's TMA (another proxy) may overwrite the mask slot only after this thread's loads from it
-        // have COMPLETED, and an mbarrier arrive does not wait for loads that were merely issued.  A shared-memory
-        // store of a value that depends on all four loads cannot issue before they return, and the arrive cannot
-        // move above a store: that is the ordering.  (`up` is idle until the epilogue.)
-        up[m] = (p[0].x + p[2].x) + (p[4].x + p[6].x);
-        mbar_arrive(SEP_BAR(kBarEmpty + wg * kFbStages + slot));
+        // The TMA (another proxy) may overwrite the mask slot only after this thread's loads from it have COMPLETED.
+        // The values stored to A2 below depend on all four loads, tcgen05.wait::st follows the stores and the arrive
+        // on a2_ready follows that: the issuing warp, which refills the slot, sees a2_ready first.
         // two half items (8 code columns each) into the two A2 buffers: the wait is for the MMAs of the
         // previous ITEM's half, committed a whole item ago
 #pragma unroll
@@ -367,8 +341,6 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
 #pragma unroll
           for (int q = 0; q < kFbChunk / 4; ++q) dst[q] = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
         }
-        c += kFbWG;
-        while (c >= C) { c -= C; ++j; }
       }
 
       // ---- sum of the warpgroups' D2_c -> overlap-add of neighbouring frames -> est ----
@@ -377,16 +349,21 @@ __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs 
         tc_fence_after();
       }
       for (int cc = wg; cc < C; cc += kFbWG) {
-        float y[16], y2[16];
-        const uint32_t dbuf = C <= 2 ? (round & 1u) : 0u;
-        __syncwarp();
-        tmem_ld16(lane_addr + kTmD2 + 2 * kFbL * (dbuf * C + cc), y);
-        tmem_ld16(lane_addr + kTmD2 + 2 * kFbL * (dbuf * C + cc) + kFbL, y2);
+        // est of source cc = the partial sums of the warpgroups that worked for it (w = cc, cc + C, ...), hi | lo halves
+        float y[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) y[e] += y2[e];
+        for (int e = 0; e < 16; ++e) y[e] = 0.f;
+        for (int w2 = cc; w2 < n_active; w2 += C) {
+          float ya[16], yb[16];
+          __syncwarp();
+          tmem_ld16(lane_addr + kTmD2 + 2 * kFbL * w2, ya);
+          tmem_ld16(lane_addr + kTmD2 + 2 * kFbL * w2 + kFbL, yb);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) y[e] += ya[e] + yb[e];
+        }
         if (cc + kFbWG >= C) {                              // this thread's last read of D2
           tc_fence_before();
-          mbar_arrive(SEP_BAR(kBarD2Free + (C <= 2 ? (round & 1u) : 0u)));
+          mbar_arrive(SEP_BAR(kBarD2Free));
         }
         // hop-block h = frame gets y[frame][0:8] + y[frame-1][8:16]
 #pragma unroll
