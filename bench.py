@@ -349,9 +349,11 @@ class Ctx:
         return float(t.item())
 
 
-def timed_replays(ctx, replay_once, est_calls=1):
-    """Warm, estimate one replay, then time R replays with R chosen so that the region is >= MIN_TIMED_MS
-    (same R on every rank).  Returns (total_ms max over ranks, R, clocks)."""
+def timed_replays(ctx, replay_once, est_calls=1, min_ms=None, yield_every=0):
+    """Warm, estimate one replay, then time R replays with R chosen so that the region is >= min_ms (default
+    MIN_TIMED_MS; same R on every rank).  Returns (total_ms max over ranks, R, clocks).  `yield_every`: a
+    Python loop of eager launches holds the GIL, and the clock sampler thread would starve: hand the GIL over
+    every so many calls (the GPU stays ahead of the host by its launch queue)."""
     torch = ctx.torch
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ctx.barrier()
@@ -361,14 +363,16 @@ def timed_replays(ctx, replay_once, est_calls=1):
     stop.record()
     torch.cuda.synchronize()
     est = ctx.max_over_ranks(start.elapsed_time(stop) / est_calls)
-    reps = max(1, int(math.ceil(MIN_TIMED_MS / max(est, 1e-3))))
+    reps = max(1, int(math.ceil((min_ms or MIN_TIMED_MS) / max(est, 1e-3))))
     sampler = ClockSampler(ctx.local)
     sampler.start()
     ctx.barrier()
     ctx.rendezvous()
     start.record()
-    for _ in range(reps):
+    for i in range(reps):
         replay_once()
+        if yield_every and i % yield_every == yield_every - 1:
+            time.sleep(0)
     stop.record()
     torch.cuda.synchronize()
     ms_total = start.elapsed_time(stop)
@@ -626,7 +630,7 @@ def filterbank_extra(ctx, batch=64, sets=2):
         state["s"] += 1
         sepcore.filterbank_separate(w, enc, dec, m, stride=stride)
 
-    ms_total, reps, clocks = timed_replays(ctx, once, est_calls=4)
+    ms_total, reps, clocks = timed_replays(ctx, once, est_calls=4, min_ms=60.0, yield_every=8)
     loop_ms = ms_total / reps
     _lib.profile_enable(True)
     for _ in range(10):
@@ -684,7 +688,7 @@ def conv1d_extra(ctx, batch=64, sets=4):
         sepcore.conv1d(data[state["s"] % sets], w, b, padding="same", activation="sigmoid")
         state["s"] += 1
 
-    ms_total, reps, clocks = timed_replays(ctx, once, est_calls=4)
+    ms_total, reps, clocks = timed_replays(ctx, once, est_calls=4, min_ms=60.0, yield_every=8)
     loop_ms = ms_total / reps
     _lib.profile_enable(True)
     for _ in range(10):
