@@ -239,14 +239,17 @@ __global__ void __launch_bounds__(kCtThreads, 1) conv1d_tc_kernel(const ConvTcAr
 //   * hand-offs: the A operand is handed over per K half (own full / empty barriers: the staging of the next tile's
 //     first half overlaps the MMAs on the second half), the accumulator is double buffered, a store warp issues the
 //     bulk stores so that no epilogue warp waits for another one, and every wait is a hardware-suspending try_wait.
-// Roles: warps 0-7 epilogue (two per 32-row quarter: columns [0, split) | [split, filters)), 8-11 staging, 12 MMA
-// issue (converged warp, one elected lane), 13 bulk stores.
+// Roles: warps 0-11 epilogue (three per 32-row quarter, a third of the columns each), 12-15 staging, 16 MMA issue
+// (converged warp, one elected lane), 17 bulk stores.
 // TMEM columns: D0 [0, NP), D1 [NP, 2 NP), A_hi [2 NP, 2 NP + K), A_lo [2 NP + K, 2 NP + 2 K)  (448 of 512 here).
-// What bounds it (in-kernel clock64 timelines and one-role-removed builds, round 2): the tensor-memory READ port.  An
-// MMA whose A operand sits in tensor memory reads its 128 x 8 words at 64 B per cycle -- 64 cycles whatever N is (so
-// two N / 2 column groups cost twice one N-wide MMA: tried, slower) -- and the epilogue's tcgen05.ld goes through the
-// same port; MMAs and the epilogue of the previous tile slow each other down to ~5500 cycles per tile against 2400
-// (MMA floor) and 2300 (MUFU floor of the sigmoids: 2 x 8 cycles per warp instruction, measured) when run alone.
+// What bounds it (in-kernel clock64 timelines, one-role-removed builds and microbenchmarks, round 2): the epilogue.  A
+// scheduler finishes one 16-column chunk per ~500 cycles whether two or three epilogue warps share it -- twice the 264
+// cycles the same code takes in isolation, where it sits on the MUFU floor (8 cycles per warp instruction, 32 per chunk)
+// -- and MMA issue (56 cycles each from the converged warp, 30 per tile), staging (~1600 cycles per K half, L2 latency
+// exposed: registers hold one half) and the epilogue wait for each other through one tile of slack.  Tried and measured
+// slower: two N / 2 accumulators with two issuing warps (60 MMAs per tile, each paying the issue cost), 32-column epilogue
+// blocks, all columns read in one tcgen05.ld burst with the accumulator released at once, half of the reciprocals on the
+// FMA pipe.
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -320,7 +323,8 @@ __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
 }
 enum : int { kC2AFull = 0, kC2AEmpty = 2, kC2DFull = 4, kC2DEmpty = 6, kC2OEmpty = 8, kC2OFull = 10, kC2Bars = 18 };
-constexpr int kCt2Threads = kCtThreads + 32;       // + the store warp
+constexpr int kC2Groups = 3;                        // epilogue warps per 32-row quarter (column groups)
+constexpr int kCt2Threads = 32 * (4 * kC2Groups + 4 + 2);   // epilogue, staging, MMA warp, store warp
 
 template <int KQ, int ACT>
 __global__ void __launch_bounds__(kCt2Threads, 1) conv1d_tc2_kernel(const ConvTcArgs a) {
@@ -339,7 +343,7 @@ __global__ void __launch_bounds__(kCt2Threads, 1) conv1d_tc2_kernel(const ConvTc
   const int64_t total_rows = static_cast<int64_t>(a.batch) * a.rows_out;
   const int n_tiles = static_cast<int>((total_rows + kCtM - 1) / kCtM);
   const uint32_t lbo_b = (NP / 8) * 128;
-  const int split = (NP / 32) * 16;                                // columns [0, split) | [split, NP): the two epilogue groups
+  const int nch = NP / 16;                                         // 16-column chunks, dealt to the epilogue column groups
   constexpr float kLog2e = 1.4426950408889634f;
 
   if (warp == 0) {
@@ -351,9 +355,9 @@ __global__ void __launch_bounds__(kCt2Threads, 1) conv1d_tc2_kernel(const ConvTc
       mbar_init(CT_BAR(kC2AFull + h), 128);
       mbar_init(CT_BAR(kC2AEmpty + h), 1);
       mbar_init(CT_BAR(kC2DFull + h), 1);
-      mbar_init(CT_BAR(kC2DEmpty + h), 256);
+      mbar_init(CT_BAR(kC2DEmpty + h), 128 * kC2Groups);
       mbar_init(CT_BAR(kC2OEmpty + h), 1);
-      for (int q = 0; q < 4; ++q) mbar_init(CT_BAR(kC2OFull + 2 * q + h), 64);
+      for (int q = 0; q < 4; ++q) mbar_init(CT_BAR(kC2OFull + 2 * q + h), 32 * kC2Groups);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -377,7 +381,7 @@ __global__ void __launch_bounds__(kCt2Threads, 1) conv1d_tc2_kernel(const ConvTc
   const uint32_t tmem = *tmem_slot;
   const uint32_t tm_a = tmem + 2 * NP;                             // A: hi K columns | lo K columns
 
-  if (warp == 13) {
+  if (warp == 4 * kC2Groups + 5) {
     // =========================== store warp: one thread hands finished quarters to the TMA engine ===========================
     if (lane == 0) {
       uint32_t i = 0;
@@ -399,7 +403,7 @@ __global__ void __launch_bounds__(kCt2Threads, 1) conv1d_tc2_kernel(const ConvTc
       }
       bulk_wait_read<0>();                                           // shared memory stays valid until the engine has read it
     }
-  } else if (warp == 12) {
+  } else if (warp == 4 * kC2Groups + 4) {
     // =========================== MMA warp: runs converged, one elected lane issues ===========================
     // ONE accumulator of N = NP columns: with the A operand in tensor memory an MMA costs max(N / 2, 64) cycles (the
     // 4 KB of A are read at the 64 B per cycle of the tensor-memory read port), so two N / 2 halves cost twice as much
@@ -428,13 +432,13 @@ __global__ void __launch_bounds__(kCt2Threads, 1) conv1d_tc2_kernel(const ConvTc
         umma_commit_elect(CT_BAR(kC2DFull + dbuf));                  // the accumulator is complete
       }
     }
-  } else if (warp >= 8 && warp < 12) {
+  } else if (warp >= 4 * kC2Groups && warp < 4 * kC2Groups + 4) {
     // =========================== staging warps: thread s = row s of the tile = TMEM lane s ===========================
-    const int s = threadIdx.x - 256;
+    const int s = threadIdx.x - 128 * kC2Groups;
     const int64_t n_x = static_cast<int64_t>(a.rows) * a.c_in;
     const int hop = a.stride * a.c_in;
     const uint32_t a_addr = tm_a + (static_cast<uint32_t>(s & ~31) << 16);
-    float4 pre[KQ];
+    float4 pre[KQ / 2];                                              // one K half of this thread's row
     auto row_of = [&](int t, const float *&xb, int64_t &g0) -> bool {
       const int64_t R = static_cast<int64_t>(t) * kCtM + s;
       const int64_t b = R / a.rows_out;
@@ -443,20 +447,20 @@ __global__ void __launch_bounds__(kCt2Threads, 1) conv1d_tc2_kernel(const ConvTc
       g0 = static_cast<int64_t>(ro) * hop - static_cast<int64_t>(a.left) * a.c_in;
       return R < total_rows;
     };
-    auto fetch = [&](int t) {
+    auto fetch_half = [&](int t, int h) {                            // (L2 hits: the tile was prefetched a tile ago)
       const float *xb;
       int64_t g0;
       const bool live = row_of(t, xb, g0);
       if (live && g0 >= 0 && g0 + K <= n_x && ((reinterpret_cast<uintptr_t>(xb + g0) & 15) == 0)) {
 #pragma unroll
-        for (int q = 0; q < KQ; ++q) pre[q] = __ldg(reinterpret_cast<const float4 *>(xb + g0) + q);
+        for (int q = 0; q < KQ / 2; ++q) pre[q] = __ldg(reinterpret_cast<const float4 *>(xb + g0) + h * (KQ / 2) + q);
       } else {
 #pragma unroll
-        for (int q = 0; q < KQ; ++q) {
+        for (int q = 0; q < KQ / 2; ++q) {
           float v[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int64_t g = g0 + 4 * q + e;
+            const int64_t g = g0 + 4 * (h * (KQ / 2) + q) + e;
             v[e] = (live && g >= 0 && g < n_x) ? __ldg(xb + g) : 0.f;   // 'same' padding / beyond the last row
           }
           pre[q] = make_float4(v[0], v[1], v[2], v[3]);
@@ -472,14 +476,14 @@ __global__ void __launch_bounds__(kCt2Threads, 1) conv1d_tc2_kernel(const ConvTc
         asm volatile("prefetch.global.L2 [%0];" :: "l"(p + 4 * K - 4));
       }
     };
-    if (blockIdx.x < n_tiles) fetch(blockIdx.x);
     prefetch_l2(blockIdx.x + gridDim.x);
     uint32_t i = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
+        fetch_half(t, h);                                            // in flight while the MMAs still read this half
         if (i > 0) {
-          mbar_wait_suspend(CT_BAR(kC2AEmpty + h), (i - 1) & 1);             // the previous tile's MMAs have read this half of A
+          mbar_wait_suspend(CT_BAR(kC2AEmpty + h), (i - 1) & 1);     // the previous tile's MMAs have read this half of A
           tc_fence_after();
         }
         __syncwarp();                                                // tcgen05.st is warp-collective
@@ -489,7 +493,7 @@ __global__ void __launch_bounds__(kCt2Threads, 1) conv1d_tc2_kernel(const ConvTc
           float hi[8], lo[8];
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
-            const float4 v = pre[2 * g + q];
+            const float4 v = pre[2 * gg + q];
             split_tf32(v.x, hi[4 * q], lo[4 * q]); split_tf32(v.y, hi[4 * q + 1], lo[4 * q + 1]);
             split_tf32(v.z, hi[4 * q + 2], lo[4 * q + 2]); split_tf32(v.w, hi[4 * q + 3], lo[4 * q + 3]);
           }
@@ -500,15 +504,16 @@ __global__ void __launch_bounds__(kCt2Threads, 1) conv1d_tc2_kernel(const ConvTc
         tc_fence_before();
         mbar_arrive(CT_BAR(kC2AFull + h));
       }
-      if (t + static_cast<int>(gridDim.x) < n_tiles) fetch(t + gridDim.x);   // the next tile's rows (L2 hits, prefetched a tile ago)
       prefetch_l2(t + 2 * gridDim.x);
     }
   } else {
     // =========================== epilogue warps: TMEM lane = row ===========================
-    // warps w (columns [0, split)) and w + 4 (columns [split, NP)) share TMEM lanes 32 (w & 3) ..
+    // warps w, w + 4, w + 8 (column groups 0, 1, 2) share TMEM lanes 32 (w & 3) ..
     const int quarter = warp & 3, grp = warp >> 2;
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
-    const int cbeg = grp ? split : 0, cend = grp ? NP : split;
+    // group g takes nch / G chunks, the first nch % G groups one more (a group may be empty: it only arrives)
+    const int cbeg = 16 * (grp * (nch / kC2Groups) + min(grp, nch % kC2Groups));
+    const int cend = cbeg + 16 * (nch / kC2Groups + (grp < nch % kC2Groups ? 1 : 0));
     uint32_t i = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
       unsigned char *otile = ob + (i & 1) * tile_bytes;
@@ -520,7 +525,7 @@ __global__ void __launch_bounds__(kCt2Threads, 1) conv1d_tc2_kernel(const ConvTc
       const uint32_t dcol = lane_addr + (i & 1) * NP + cbeg;
       // chunks of 16 columns that exist in full, then `rem` more columns; up to 4 of those (the reference's 129th
       // column) ride with the last full chunk instead of costing a chunk of their own
-      const int cols = min(cend, a.filters) - cbeg, full = cols >> 4, rem = cols & 15;
+      const int cols = max(0, min(cend, a.filters) - cbeg), full = cols >> 4, rem = cols & 15;
       const bool ride = rem > 0 && rem <= 4 && full > 0;
       const int n_chunks = full + ((rem > 0 && !ride) ? 1 : 0);
       // 16 columns of this row.  The order of the special-function instructions is PINNED (asm volatile): 16 x EX2, then
@@ -566,8 +571,11 @@ __global__ void __launch_bounds__(kCt2Threads, 1) conv1d_tc2_kernel(const ConvTc
         tmem_ld16_wait(r);
         if (ride && ch == full - 1) tmem_ld4_wait(rx);
       };
-      load_chunk(0, r0);
-      wait_chunk(0, r0);
+      if (n_chunks == 0) drained();                                  // nothing to read for this group
+      else {
+        load_chunk(0, r0);
+        wait_chunk(0, r0);
+      }
 #pragma unroll 1
       for (int it = 0; it < n_chunks; it += 2) {                     // two chunks per trip: the register sets alternate
         const bool second = it + 1 < n_chunks, third = it + 2 < n_chunks;
@@ -630,9 +638,8 @@ int conv1d_tc_try(const float *d_x, const float *d_w, const float *d_b, int batc
     SEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
     const int64_t tiles = (static_cast<int64_t>(batch) * rows_out + kCtM - 1) / kCtM;
     const int grid = static_cast<int>(std::min<int64_t>(tiles, sms));
-    profile_begin(stream, "conv1d_tc2_kernel<K=%d> (tcgen05 kind::tf32 x3, A in TMEM x2, M=128 N=%d+%d, output tiles by "
-                  "cp.async.bulk; taps=%d c_in=%d filters=%d stride=%d)", K, (NP / 32) * 16, NP - (NP / 32) * 16, taps, c_in,
-                  filters, stride);
+    profile_begin(stream, "conv1d_tc2_kernel<K=%d> (tcgen05 kind::tf32 x3, A in TMEM x2, M=128 N=%d, output tiles by "
+                  "cp.async.bulk; taps=%d c_in=%d filters=%d stride=%d)", K, NP, taps, c_in, filters, stride);
     kern<<<grid, kCt2Threads, smem2, stream>>>(a);
     profile_end(stream);
     SEP_LAUNCHED();

@@ -720,6 +720,8 @@ def test_conv1d_reference_shape(sep, oracle):
     (7, 1002, 40, 2, 129, 1, "same", "relu"),        # 7014 rows: the last tile ends inside a quarter, 16-byte multiple
     (6, 900, 40, 2, 64, 1, "same", "sigmoid"),       # even filter count: the first tcgen05 kernel (transposing epilogue)
     (4, 2100, 20, 4, 131, 2, "valid", None),         # K = 80 from 4 taps x 20 channels, stride 2, no activation
+    (9, 600, 40, 2, 17, 1, "same", "sigmoid"),       # 17 filters: two 16-column chunks for three epilogue groups (one idles)
+    (5, 1000, 40, 2, 155, 1, "same", "relu"),        # 155 filters: 10 chunks, 11 live columns in the last one
     (3, 4000, 1, 16, 64, 8, "valid", "relu"),        # strided frames (an encoder-shaped call), 4 columns per thread
     (2, 2500, 7, 5, 33, 2, "same", None),
     (4, 1200, 8, 4, 134, 2, "same", "relu"),         # 128 + 6 tail columns: the 8 x 8 micro-tile kernel with REM = 8
