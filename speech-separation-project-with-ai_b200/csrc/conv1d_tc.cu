@@ -65,7 +65,9 @@ __global__ void __launch_bounds__(kCtThreads, 1) conv1d_tc_kernel(const ConvTcAr
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
   const uint32_t bar0 = smem_u32(bars), sm0 = smem_u32(sm);
 #define CT_BAR(i) (bar0 + 8u * static_cast<uint32_t>(i))
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the warp index through a shuffle: ptxas then KNOWS that it is warp-uniform, so the role branches are uniform and the
+  // addresses / descriptors of the MMA warps can live in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int tiles_per = (a.rows_out + kCtM - 1) / kCtM, n_tiles = a.batch * tiles_per;
   const uint32_t lbo_a = (kCtM / 8) * 128, lbo_b = (NP / 8) * 128;
 
@@ -339,7 +341,9 @@ __global__ void __launch_bounds__(kCt2Threads, 1) conv1d_tc2_kernel(const ConvTc
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + kC2Bars);
   const uint32_t bar0 = smem_u32(bars), sm0 = smem_u32(sm);
 #define CT_BAR(i) (bar0 + 8u * static_cast<uint32_t>(i))
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the warp index through a shuffle: ptxas then KNOWS that it is warp-uniform, so the role branches are uniform and the
+  // addresses / descriptors of the MMA warps can live in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int64_t total_rows = static_cast<int64_t>(a.batch) * a.rows_out;
   const int n_tiles = static_cast<int>((total_rows + kCtM - 1) / kCtM);
   const uint32_t lbo_b = (NP / 8) * 128;

@@ -100,7 +100,9 @@ enum : int {
 __global__ void __launch_bounds__(kFbThreads, 1) filterbank_kernel(const FbArgs a,
                                                                    const __grid_constant__ CUtensorMap mask_map) {
   extern __shared__ __align__(128) unsigned char sm[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the warp index through a shuffle: ptxas then KNOWS that it is warp-uniform, so the role branches are uniform and the
+  // addresses / descriptors of the MMA warps can live in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int wg = threadIdx.x >> 7, m = threadIdx.x & 127, wq = warp & 3;
   const int K = a.frames, C = a.n_src;
   uint64_t *bars = reinterpret_cast<uint64_t *>(sm + kOffBar);
