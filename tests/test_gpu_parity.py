@@ -857,7 +857,7 @@ def test_single_launch_finalisation_matches(sep, oracle, monkeypatch):
 
 
 # ----------------------------------------------------------------- cfg5: tcgen05 filterbank
-@pytest.mark.parametrize("n,n_src", [(1040, 1), (2000, 2), (32000, 2), (16 + 8 * 127, 3), (16 + 8 * 254, 2)])
+@pytest.mark.parametrize("n,n_src", [(1040, 1), (2000, 2), (32000, 2), (16 + 8 * 127, 3), (16 + 8 * 254, 2), (3000, 4)])
 def test_filterbank_tcgen05_matches_oracle(sep, oracle, n, n_src):
     """Encoder -> relu -> mask -> decoder -> overlap-add on the tensor cores (3xTF32) against
     the float64 oracle: fp32-level agreement (1e-4 of the array scale, 1e-5 relative L2)."""
