@@ -17,9 +17,9 @@ ap.add_argument("--sources", type=int, default=2)
 ap.add_argument("--size", type=int, default=256)
 ap.add_argument("--shift", type=int, default=128)
 a = ap.parse_args()
-args = argparse.Namespace(batch=64, seconds=4.0, sources=a.sources, size=a.size, shift=a.shift, window="blackman")
-d = {k: torch.from_numpy(v).cuda() for k, v in bench.make_set(args, seed=3).items()}
-kw = dict(size=a.size, shift=a.shift, window=bench.window_fn("blackman"))
+wl = bench.Workload("stress", 64, 4.0, a.sources, a.size, a.shift, "blackman")
+d = {k: torch.from_numpy(v).cuda() for k, v in wl.make_set(seed=3).items()}
+kw = wl.kw()
 ref = sepcore.separate_and_score(d["mix"], d["masks"], d["refs"], **kw)
 torch.cuda.synchronize()
 r0, e0, s0 = ref["scores"].clone(), ref["est"].clone(), ref["sums"].clone()
