@@ -221,9 +221,14 @@ __global__ void __launch_bounds__(W * 32, CPS) wstrip512_kernel(const FusedArgs 
       for (int k = 0; k < 6; ++k) carry[i][k] = make_float2(0.f, 0.f);
     }
 #pragma unroll
-    for (int i = 0; i < G::NPIT; ++i) pit2[32 * i] = make_float2(0.f, 0.f);
+    float2 pitr[G::NPIT > 0 ? G::NPIT : 1];                          // PIT pair sums of this lane (registers: 8 warps per SM leave room)
+#pragma unroll
+    for (int i = 0; i < G::NPIT; ++i) pitr[i] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < G::NACC; ++i) acc[32 * i] = 0.0;
+    double accr[SCORE ? 2 * C : 1];                                  // |e_i|^2, |r_i|^2 of this lane: registers
+#pragma unroll
+    for (int i = 0; i < (SCORE ? 2 * C : 1); ++i) accr[i] = 0.0;
 
     int slot0 = 0;                                                  // ring slot of hop block ta
 #pragma unroll 1
@@ -293,8 +298,7 @@ __global__ void __launch_bounds__(W * 32, CPS) wstrip512_kernel(const FusedArgs 
         const float2 own2 = make_float2(own_w, own_w);
 #pragma unroll
         for (int i = 0; i < C; ++i) {                               // column j of the pair sums
-          float2 *dst = pit2 + 32 * (i * C + j);
-          *dst = __ffma2_rn(pj[i], own2, *dst);
+          pitr[i * C + j] = __ffma2_rn(pj[i], own2, pitr[i * C + j]);
         }
       };
       auto mixture_spectra = [&]() {
@@ -439,8 +443,8 @@ __global__ void __launch_bounds__(W * 32, CPS) wstrip512_kernel(const FusedArgs 
           double ee = 0.0, rr = 0.0;
 #pragma unroll
           for (int k = 0; k < 4; ++k) { ee = fma(e[i][k], e[i][k], ee); rr = fma(r[i][k], r[i][k], rr); }
-          acc[32 * (C * C + i)] += ee;
-          acc[32 * (C * C + C + i)] += rr;
+          accr[i] += ee;
+          accr[C + i] += rr;
 #pragma unroll
           for (int j = 0; j < C; ++j) {
             double gq = 0.0;
@@ -488,11 +492,13 @@ __global__ void __launch_bounds__(W * 32, CPS) wstrip512_kernel(const FusedArgs 
       double vals[NV];
 #pragma unroll
       for (int i = 0; i < C * C; ++i) {
-        const float2 pp = pit2[32 * i];
+        const float2 pp = pitr[i];
         vals[i] = static_cast<double>(pp.x) + static_cast<double>(pp.y);
       }
 #pragma unroll
-      for (int i = 0; i < G::NACC; ++i) vals[C * C + i] = acc[32 * i];
+      for (int i = 0; i < C * C; ++i) vals[C * C + i] = acc[32 * i];
+#pragma unroll
+      for (int i = 0; i < 2 * C; ++i) vals[2 * C * C + i] = accr[i];
 #pragma unroll
       for (int i = 0; i < NV; ++i) vals[i] = warp_sum(vals[i]);
       if (lane == 0) {
