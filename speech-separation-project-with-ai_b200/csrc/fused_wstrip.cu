@@ -182,7 +182,9 @@ __global__ void __launch_bounds__(W * 32, CPS) wstrip256_kernel(const FusedArgs 
       for (int k = 0; k < NCARRY; ++k) carry[i][k] = 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < G::NPIT; ++i) pit2[32 * i] = make_float2(0.f, 0.f);
+    float2 pitr[G::NPIT > 0 ? G::NPIT : 1];                       // PIT pair sums of this lane
+#pragma unroll
+    for (int i = 0; i < G::NPIT; ++i) pitr[i] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < G::NACC; ++i) acc[32 * i] = 0.0;
 
@@ -291,8 +293,7 @@ __global__ void __launch_bounds__(W * 32, CPS) wstrip256_kernel(const FusedArgs 
           if (!anyzero) bins(std::false_type{}); else bins(std::true_type{});
 #pragma unroll
           for (int i = 0; i < C; ++i) {                             // column j of the pair sums
-            float2 *dst = pit2 + 32 * (i * C + j);
-            *dst = __ffma2_rn(pj[i], own2, *dst);
+            pitr[i * C + j] = __ffma2_rn(pj[i], own2, pitr[i * C + j]);
           }
         };
         if constexpr (C == 2 && DUAL) {
@@ -479,7 +480,7 @@ __global__ void __launch_bounds__(W * 32, CPS) wstrip256_kernel(const FusedArgs 
       double vals[NV];
 #pragma unroll
       for (int i = 0; i < C * C; ++i) {
-        const float2 pp = pit2[32 * i];
+        const float2 pp = pitr[i];
         vals[i] = static_cast<double>(pp.x) + static_cast<double>(pp.y);
       }
 #pragma unroll
