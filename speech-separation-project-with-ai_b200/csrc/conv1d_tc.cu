@@ -234,9 +234,9 @@ __global__ void __launch_bounds__(kCtThreads, 1) conv1d_tc_kernel(const ConvTcAr
 //   * the A operand (the tile's im2col rows, hi | lo) lives in TENSOR MEMORY (lane = row; the staging thread that owns
 //     a row writes it with tcgen05.st), which frees the shared memory for two output tiles;
 //   * the epilogue thread of a row applies the activation and stores its values into a shared-memory image of the
-//     output tile (pitch = filters floats, odd, so the 32 rows of a warp hit 32 different banks); when the two warps of
-//     a 32-row quarter are done, one thread hands the quarter (32 * filters * 4 bytes, contiguous in HBM) to the TMA
-//     engine (cp.async.bulk shared -> global).  No transposes, no per-element global stores;
+//     output tile (pitch = filters floats, odd, so the 32 rows of a warp hit 32 different banks); when the three warps
+//     of a 32-row quarter are done, the store warp hands the quarter (32 * filters * 4 bytes, contiguous in HBM) to the
+//     TMA engine (cp.async.bulk shared -> global).  No transposes, no per-element global stores;
 //   * the bias is folded into the activation's first FFMA (sigmoid: ex2(d * -log2e - bias * log2e));
 //   * hand-offs: the A operand is handed over per K half (own full / empty barriers: the staging of the next tile's
 //     first half overlaps the MMAs on the second half), the accumulator is double buffered, a store warp issues the
@@ -248,10 +248,13 @@ __global__ void __launch_bounds__(kCtThreads, 1) conv1d_tc_kernel(const ConvTcAr
 // scheduler finishes one 16-column chunk per ~500 cycles whether two or three epilogue warps share it -- twice the 264
 // cycles the same code takes in isolation, where it sits on the MUFU floor (8 cycles per warp instruction, 32 per chunk)
 // -- and MMA issue (56 cycles each from the converged warp, 30 per tile), staging (~1600 cycles per K half, L2 latency
-// exposed: registers hold one half) and the epilogue wait for each other through one tile of slack.  Tried and measured
-// slower: two N / 2 accumulators with two issuing warps (60 MMAs per tile, each paying the issue cost), 32-column epilogue
+// exposed: registers hold one half) and the epilogue wait for each other through one tile of slack.  With the same roles
+// running UNSYNCHRONISED (tools/ubench/epilogue_ldtm.cu) a scheduler finishes a chunk per 280-297 cycles next to
+// full-rate MMAs, tile stores and staging: no shared unit is the limit, the hand-offs are.  Tried and measured slower or
+// equal: two N / 2 accumulators with two issuing warps (60 MMAs per tile, each paying the issue cost), 32-column epilogue
 // blocks, all columns read in one tcgen05.ld burst with the accumulator released at once, half of the reciprocals on the
-// FMA pipe.
+// FMA pipe, a software-pipelined epilogue (EX2 of chunk c next to RCP of chunk c - 1), staggered group starts, two
+// staging sets (one per K half, 80 registers).
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
