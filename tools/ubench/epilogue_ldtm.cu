@@ -23,6 +23,7 @@ __global__ void k(float *out, int iters, long long *cyc, int mma_warp, int work_
   __shared__ uint32_t slot;
   __shared__ volatile int done;
   __shared__ uint64_t mbar;
+  __shared__ uint64_t dummy[2];
   float *nb = sm, *ob = sm + 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0) {
@@ -30,7 +31,7 @@ __global__ void k(float *out, int iters, long long *cyc, int mma_warp, int work_
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   for (int i = threadIdx.x; i < 256; i += blockDim.x) nb[i] = 0.01f * i;
-  if (threadIdx.x == 0) { done = 0; mbar_init(smem_u32(&mbar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (threadIdx.x == 0) { done = 0; mbar_init(smem_u32(&mbar), 1); mbar_init(smem_u32(&dummy[0]), 384); mbar_init(smem_u32(&dummy[1]), 96); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   // B operand region for the MMA warp: 48 KB behind the output rows
   float *bop = ob + 8 * 32 * 129;
   for (int i = threadIdx.x; i < 12 * 1024; i += blockDim.x) bop[i] = 0.001f * (i & 63);
@@ -126,6 +127,13 @@ __global__ void k(float *out, int iters, long long *cyc, int mma_warp, int work_
   };
   long long t0 = clock64();
   for (int it = 0; it < iters; it += 2) {
+    if ((mma_warp & 8) && (it % 3) == 0) {                      // the kernel's per-tile fences and arrives
+      tc_fence_before();
+      mbar_arrive(smem_u32(&dummy[0]));
+      fence_async_smem();
+      mbar_arrive(smem_u32(&dummy[1]));
+      tc_fence_after();
+    }
     if (LD == 1) ld16_issue(lane_addr + 16, r1);
     if (LD == 2) { ld16_issue(lane_addr, r0); ld16_wait(r0); }
     chunk(r0, 0);
@@ -151,7 +159,7 @@ int main() {
   const size_t smem = (256 + 8 * 32 * 129) * 4 + 48 * 1024;
   cudaFuncSetAttribute(k<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  for (int mma = 3; mma < 8; mma += 4)
+  for (int mma = 7; mma < 16; mma += 8)
   for (int ld = 1; ld < 2; ++ld)
     for (int warps = 8; warps <= 12; warps += 4) {
       for (int rep = 0; rep < 2; ++rep) {
@@ -163,7 +171,7 @@ int main() {
       }
       cudaMemcpy(h, cyc, 32, cudaMemcpyDeviceToHost);
       printf("%s, %s, %2d warps per SM: %.0f cycles per chunk and warp = %.0f per chunk and scheduler (MMA batches of 30: %lld, %.0f cycles per MMA; 66 KB tile stores: %lld; staging halves: %lld)\n",
-             mma == 3 ? "MMA + store warps" : "MMA + store + 4 staging warps", ld == 0 ? "no tcgen05.ld" : "tcgen05.ld one chunk ahead", warps,
+             mma == 7 ? "MMA + store + staging warps" : "MMA + store + staging warps + per-tile fences / arrives", ld == 0 ? "no tcgen05.ld" : "tcgen05.ld one chunk ahead", warps,
              (double)h[0] / iters, (double)h[0] / iters / (warps / 4.0), h[1], h[1] ? (double)h[0] / (30.0 * h[1]) : 0.0, h[2], h[3]);
     }
   return 0;
