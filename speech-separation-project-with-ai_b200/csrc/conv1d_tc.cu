@@ -369,13 +369,25 @@ __global__ void __launch_bounds__(kCt2Threads, 1) conv1d_tc2_kernel(const ConvTc
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // weights W [K][filters] row-major -> B[n][k] (N rows, K-major), split hi / lo; columns beyond `filters` are zero
-  for (int e = threadIdx.x; e < K * NP; e += kCt2Threads) {
-    const int k = e / NP, n = e - k * NP;
-    float hi = 0.f, lo = 0.f;
-    if (n < a.filters) split_tf32(__ldg(a.w + static_cast<int64_t>(k) * a.filters + n), hi, lo);
-    const int o = kmajor_off(n, k, NP / 8);
-    *reinterpret_cast<float *>(Bhi + o) = hi;
-    *reinterpret_cast<float *>(Blo + o) = lo;
+  // (eight loads in flight per thread: a one-load-at-a-time loop took 5 us of every launch)
+  for (int e0 = threadIdx.x; e0 < K * NP; e0 += 8 * kCt2Threads) {
+    float wv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = e0 + u * kCt2Threads, k = e / NP, n = e - k * NP;
+      wv[u] = (e < K * NP && n < a.filters) ? __ldg(a.w + static_cast<int64_t>(k) * a.filters + n) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = e0 + u * kCt2Threads, k = e / NP, n = e - k * NP;
+      if (e < K * NP) {
+        float hi, lo;
+        split_tf32(wv[u], hi, lo);
+        const int o = kmajor_off(n, k, NP / 8);
+        *reinterpret_cast<float *>(Bhi + o) = hi;
+        *reinterpret_cast<float *>(Blo + o) = lo;
+      }
+    }
   }
   for (int n = threadIdx.x; n < NP + 32; n += kCt2Threads) {
     const float bv = (a.bias && n < a.filters) ? __ldg(a.bias + n) : 0.f;
