@@ -327,21 +327,30 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
 }
-enum : int { kC2AFull = 0, kC2AEmpty = 2, kC2DFull = 4, kC2DEmpty = 6, kC2OEmpty = 8, kC2OFull = 10, kC2Bars = 18 };
+enum : int { kC2AFull = 0, kC2AEmpty = 2, kC2DFull = 4, kC2DEmpty = 6, kC2OEmpty = 8, kC2OFull = 10, kC2Bars = 18,
+              // XS layout: six output quarter slots and the x tile
+              kC3OEmpty = 8, kC3OFull = 14, kC3XFull = 20, kC3Bars = 21, kC3Slots = 6 };
 constexpr int kC2Groups = 3;                        // epilogue warps per 32-row quarter (column groups)
 constexpr int kCt2Threads = 32 * (4 * kC2Groups + 4 + 2);   // epilogue, staging, MMA warp, store warp
 
-template <int KQ, int ACT>
+// XS = true (the reference geometry: two taps, stride 1, no left padding): the x rows of a tile are ONE contiguous span (row r
+// is floats [40 r, 40 r + 80): its second K half is the first K half of row r + 1), brought into shared memory by one
+// cp.async.bulk instead of 20 LDG.128 per thread whose lanes are 160 bytes apart (32 sectors per request: as many LSU
+// wavefronts as the whole epilogue), and the output image shrinks from two tiles to a ring of six 32-row quarters to make
+// room for it.
+template <int KQ, int ACT, bool XS>
 __global__ void __launch_bounds__(kCt2Threads, 1) conv1d_tc2_kernel(const ConvTcArgs a) {
   static_assert(KQ % 4 == 0, "the staging threads write 8 columns of tensor memory at a time, per K half");
   extern __shared__ __align__(128) unsigned char sm[];
   constexpr int K = 4 * KQ;
   const int NP = a.npad, bbytes = KQ * (NP / 8) * 128;             // one B operand
   const int tile_bytes = kCtM * a.filters * 4, qbytes = 32 * a.filters * 4;
-  unsigned char *Bhi = sm, *Blo = sm + bbytes, *ob = Blo + bbytes; // two output tiles behind the weights
-  float *nb = reinterpret_cast<float *>(ob + 2 * tile_bytes);      // per column: the bias term of the activation
+  unsigned char *Bhi = sm, *Blo = sm + bbytes, *ob = Blo + bbytes; // output image behind the weights: two tiles / six quarters
+  const int xbytes = XS ? ((kCtM + 1) * a.c_in * 4 + 127) / 128 * 128 : 0;
+  unsigned char *xbuf = ob + (XS ? kC3Slots * qbytes : 2 * tile_bytes);   // XS: rows R0 .. R0 + 128 of x, contiguous
+  float *nb = reinterpret_cast<float *>(xbuf + xbytes);            // per column: the bias term of the activation
   uint64_t *bars = reinterpret_cast<uint64_t *>(nb + NP + 32);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + kC2Bars);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + (XS ? kC3Bars : kC2Bars));
   const uint32_t bar0 = smem_u32(bars), sm0 = smem_u32(sm);
 #define CT_BAR(i) (bar0 + 8u * static_cast<uint32_t>(i))
   // the warp index through a shuffle: ptxas then KNOWS that it is warp-uniform, so the role branches are uniform and the
@@ -363,8 +372,17 @@ __global__ void __launch_bounds__(kCt2Threads, 1) conv1d_tc2_kernel(const ConvTc
       mbar_init(CT_BAR(kC2AEmpty + h), 1);
       mbar_init(CT_BAR(kC2DFull + h), 1);
       mbar_init(CT_BAR(kC2DEmpty + h), 128 * kC2Groups);
-      mbar_init(CT_BAR(kC2OEmpty + h), 1);
-      for (int q = 0; q < 4; ++q) mbar_init(CT_BAR(kC2OFull + 2 * q + h), 32 * kC2Groups);
+      if (!XS) {
+        mbar_init(CT_BAR(kC2OEmpty + h), 1);
+        for (int q = 0; q < 4; ++q) mbar_init(CT_BAR(kC2OFull + 2 * q + h), 32 * kC2Groups);
+      }
+    }
+    if (XS) {
+      for (int sl = 0; sl < kC3Slots; ++sl) {
+        mbar_init(CT_BAR(kC3OEmpty + sl), 1);
+        mbar_init(CT_BAR(kC3OFull + sl), 32 * kC2Groups);
+      }
+      mbar_init(CT_BAR(kC3XFull), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -402,7 +420,27 @@ __global__ void __launch_bounds__(kCt2Threads, 1) conv1d_tc2_kernel(const ConvTc
 
   if (warp == 4 * kC2Groups + 5) {
     // =========================== store warp: one thread hands finished quarters to the TMA engine ===========================
-    if (lane == 0) {
+    if (lane == 0 && XS) {
+      // one bulk group per 32-row quarter; a slot is free again once the group that read it is two groups back
+      uint32_t n = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int q = 0; q < 4; ++q, ++n) {
+          const uint32_t slot = n % kC3Slots;
+          mbar_wait_suspend(CT_BAR(kC3OFull + slot), (n / kC3Slots) & 1);       // all column groups have written these 32 rows
+          const int64_t R0 = static_cast<int64_t>(t) * kCtM + q * 32;
+          const int rows_here = static_cast<int>(std::min<int64_t>(32, total_rows - R0));
+          const uint32_t bytes = static_cast<uint32_t>(rows_here > 0 ? rows_here : 0) * a.filters * 4u;
+          if (bytes > 0 && (bytes & 15u) == 0)                       // (a ragged last quarter is stored by its writers)
+            bulk_store(a.out + R0 * a.filters, smem_u32(ob + slot * qbytes), bytes);
+          bulk_commit();
+          if (n >= 2) {
+            bulk_wait_read<2>();                                     // group n - 2 has been read:
+            mbar_arrive(CT_BAR(kC3OEmpty + (n - 2) % kC3Slots));     // the epilogue may write its slot again
+          }
+        }
+      }
+      bulk_wait_read<0>();                                           // shared memory stays valid until the engine has read it
+    } else if (lane == 0) {
       uint32_t i = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
         if (i > 0) {
@@ -411,7 +449,7 @@ __global__ void __launch_bounds__(kCt2Threads, 1) conv1d_tc2_kernel(const ConvTc
         }
         unsigned char *otile = ob + (i & 1) * tile_bytes;
         for (int q = 0; q < 4; ++q) {
-          mbar_wait_suspend(CT_BAR(kC2OFull + 2 * q + (i & 1)), (i >> 1) & 1);   // both column groups have written these 32 rows
+          mbar_wait_suspend(CT_BAR(kC2OFull + 2 * q + (i & 1)), (i >> 1) & 1);   // all column groups have written these 32 rows
           const int64_t R0 = static_cast<int64_t>(t) * kCtM + q * 32;
           const int rows_here = static_cast<int>(std::min<int64_t>(32, total_rows - R0));
           const uint32_t bytes = static_cast<uint32_t>(rows_here > 0 ? rows_here : 0) * a.filters * 4u;
@@ -495,35 +533,88 @@ __global__ void __launch_bounds__(kCt2Threads, 1) conv1d_tc2_kernel(const ConvTc
         asm volatile("prefetch.global.L2 [%0];" :: "l"(p + 4 * K - 4));
       }
     };
-    prefetch_l2(blockIdx.x + gridDim.x);
-    uint32_t i = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+    if constexpr (XS) {
+      // the tile's rows R0 .. R0 + 128 of x are one contiguous run of floats [40 R0, 40 (R0 + 129)): one bulk copy (clipped at
+      // the end of x); thread s reads K half h of its row at chunk s + h of the buffer
+      const int64_t x_floats = static_cast<int64_t>(a.batch) * n_x;
+      const int chunk = a.c_in * 4;                                  // bytes of a K half (one row of x)
+      auto issue_x = [&](int t) {                                    // one thread
+        const int64_t f0 = static_cast<int64_t>(t) * kCtM * a.c_in;
+        const uint32_t bytes = static_cast<uint32_t>(std::min<int64_t>((kCtM + 1) * a.c_in, x_floats - f0) * 4);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the buffer's readers are done (barrier below)
+        mbar_expect_tx(CT_BAR(kC3XFull), bytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(smem_u32(xbuf)), "l"(a.x + f0), "r"(bytes), "r"(CT_BAR(kC3XFull)) : "memory");
+      };
+      if (s == 0 && blockIdx.x < n_tiles) issue_x(blockIdx.x);
+      uint32_t i = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+        const int64_t R = static_cast<int64_t>(t) * kCtM + s;
+        const bool live = R < total_rows;
+        const bool last_row = live && (R % a.rows_out) == a.rows_out - 1;   // 'same': its second tap is the zero row
+        mbar_wait_suspend(CT_BAR(kC3XFull), i & 1);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        fetch_half(t, h);                                            // in flight while the MMAs still read this half
-        if (i > 0) {
-          mbar_wait_suspend(CT_BAR(kC2AEmpty + h), (i - 1) & 1);     // the previous tile's MMAs have read this half of A
-          tc_fence_after();
-        }
-        __syncwarp();                                                // tcgen05.st is warp-collective
+        for (int h = 0; h < 2; ++h) {
+          const float4 *src = reinterpret_cast<const float4 *>(xbuf + (s + h) * chunk);
+          const bool zero = !live || (h == 1 && last_row);
 #pragma unroll
-        for (int gg = 0; gg < KQ / 4; ++gg) {
-          const int g = h * (KQ / 4) + gg;
-          float hi[8], lo[8];
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const float4 v = pre[2 * gg + q];
-            split_tf32(v.x, hi[4 * q], lo[4 * q]); split_tf32(v.y, hi[4 * q + 1], lo[4 * q + 1]);
-            split_tf32(v.z, hi[4 * q + 2], lo[4 * q + 2]); split_tf32(v.w, hi[4 * q + 3], lo[4 * q + 3]);
+          for (int q = 0; q < KQ / 2; ++q) pre[q] = zero ? make_float4(0.f, 0.f, 0.f, 0.f) : src[q];
+          if (i > 0) {
+            mbar_wait_suspend(CT_BAR(kC2AEmpty + h), (i - 1) & 1);   // the previous tile's MMAs have read this half of A
+            tc_fence_after();
           }
-          tmem_st8(a_addr + 8 * g, hi);
-          tmem_st8(a_addr + K + 8 * g, lo);
+          __syncwarp();                                              // tcgen05.st is warp-collective
+#pragma unroll
+          for (int gg = 0; gg < KQ / 4; ++gg) {
+            const int g = h * (KQ / 4) + gg;
+            float hi[8], lo[8];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const float4 v = pre[2 * gg + q];
+              split_tf32(v.x, hi[4 * q], lo[4 * q]); split_tf32(v.y, hi[4 * q + 1], lo[4 * q + 1]);
+              split_tf32(v.z, hi[4 * q + 2], lo[4 * q + 2]); split_tf32(v.w, hi[4 * q + 3], lo[4 * q + 3]);
+            }
+            tmem_st8(a_addr + 8 * g, hi);
+            tmem_st8(a_addr + K + 8 * g, lo);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(CT_BAR(kC2AFull + h));
         }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(CT_BAR(kC2AFull + h));
+        asm volatile("bar.sync 1, 128;" ::: "memory");               // every staging thread has read the buffer
+        if (s == 0 && t + static_cast<int>(gridDim.x) < n_tiles) issue_x(t + gridDim.x);
       }
-      prefetch_l2(t + 2 * gridDim.x);
+    } else {
+    prefetch_l2(blockIdx.x + gridDim.x);
+      uint32_t i = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+  #pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          fetch_half(t, h);                                            // in flight while the MMAs still read this half
+          if (i > 0) {
+            mbar_wait_suspend(CT_BAR(kC2AEmpty + h), (i - 1) & 1);     // the previous tile's MMAs have read this half of A
+            tc_fence_after();
+          }
+          __syncwarp();                                                // tcgen05.st is warp-collective
+  #pragma unroll
+          for (int gg = 0; gg < KQ / 4; ++gg) {
+            const int g = h * (KQ / 4) + gg;
+            float hi[8], lo[8];
+  #pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const float4 v = pre[2 * gg + q];
+              split_tf32(v.x, hi[4 * q], lo[4 * q]); split_tf32(v.y, hi[4 * q + 1], lo[4 * q + 1]);
+              split_tf32(v.z, hi[4 * q + 2], lo[4 * q + 2]); split_tf32(v.w, hi[4 * q + 3], lo[4 * q + 3]);
+            }
+            tmem_st8(a_addr + 8 * g, hi);
+            tmem_st8(a_addr + K + 8 * g, lo);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(CT_BAR(kC2AFull + h));
+        }
+        prefetch_l2(t + 2 * gridDim.x);
+      }
     }
   } else {
     // =========================== epilogue warps: TMEM lane = row ===========================
@@ -535,9 +626,14 @@ __global__ void __launch_bounds__(kCt2Threads, 1) conv1d_tc2_kernel(const ConvTc
     const int cend = cbeg + 16 * (nch / kC2Groups + (grp < nch % kC2Groups ? 1 : 0));
     uint32_t i = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
-      unsigned char *otile = ob + (i & 1) * tile_bytes;
+      const uint32_t qn = 4 * i + quarter, slot = qn % kC3Slots;      // XS: this quarter's slot of the output ring
+      unsigned char *otile = XS ? ob + slot * qbytes - quarter * qbytes : ob + (i & 1) * tile_bytes;   // (+ quarter * qbytes below)
       float *orow = reinterpret_cast<float *>(otile) + (quarter * 32 + lane) * a.filters;
-      if (i > 1) mbar_wait_suspend(CT_BAR(kC2OEmpty + (i & 1)), ((i >> 1) - 1) & 1);   // the store of tile i - 2 has read this buffer
+      if constexpr (XS) {
+        if (qn >= kC3Slots) mbar_wait_suspend(CT_BAR(kC3OEmpty + slot), (qn / kC3Slots - 1) & 1);   // the store that read this slot is done
+      } else {
+        if (i > 1) mbar_wait_suspend(CT_BAR(kC2OEmpty + (i & 1)), ((i >> 1) - 1) & 1);   // the store of tile i - 2 has read this buffer
+      }
       mbar_wait_suspend(CT_BAR(kC2DFull + (i & 1)), (i >> 1) & 1);
       tc_fence_after();
       uint32_t r0[16], r1[16], rx[4];
@@ -618,7 +714,7 @@ __global__ void __launch_bounds__(kCt2Threads, 1) conv1d_tc2_kernel(const ConvTc
           for (int c = cbeg; c < cend && c < a.filters; ++c) grow[c] = orow[c];
       }
       fence_async_smem();                                            // this thread's tile values -> visible to the TMA engine
-      mbar_arrive(CT_BAR(kC2OFull + 2 * quarter + (i & 1)));
+      mbar_arrive(CT_BAR(XS ? kC3OFull + slot : kC2OFull + 2 * quarter + (i & 1)));
     }
   }
   tc_fence_before();
@@ -651,15 +747,27 @@ int conv1d_tc_try(const float *d_x, const float *d_w, const float *d_b, int batc
   if (!v1_only && (filters & 1) && NP >= 32 && 2 * NP + 2 * K <= 512 && smem2 <= 227 * 1024 &&
       (reinterpret_cast<uintptr_t>(d_out) & 15) == 0) {
     *handled = true;
-    void (*kern)(ConvTcArgs) = act == SEP_ACT_SIGMOID ? conv1d_tc2_kernel<KQ, SEP_ACT_SIGMOID>
-                               : act == SEP_ACT_RELU  ? conv1d_tc2_kernel<KQ, SEP_ACT_RELU>
-                                                      : conv1d_tc2_kernel<KQ, SEP_ACT_LINEAR>;
-    SEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
+    // the reference geometry (two taps, stride 1, 'same' with the pad on the right) takes the x tile by one bulk copy
+    const char *xs_env = getenv("SEPCORE_CONV_XS");
+    const bool xs = !(xs_env && atoi(xs_env) == 0) && taps == 2 && stride == 1 && left == 0 && rows_out == rows &&
+                    (reinterpret_cast<uintptr_t>(d_x) & 15) == 0 && (c_in * 4) % 16 == 0;
+    const size_t smem3 = 2 * static_cast<size_t>(KQ) * (NP / 8) * 128 + kC3Slots * 32 * static_cast<size_t>(filters) * 4 +
+                         ((kCtM + 1) * static_cast<size_t>(c_in) * 4 + 127) / 128 * 128 + static_cast<size_t>(NP + 32) * 4 +
+                         8 * kC3Bars + 64;
+    void (*kern)(ConvTcArgs);
+    if (xs) kern = act == SEP_ACT_SIGMOID ? conv1d_tc2_kernel<KQ, SEP_ACT_SIGMOID, true>
+                   : act == SEP_ACT_RELU  ? conv1d_tc2_kernel<KQ, SEP_ACT_RELU, true>
+                                          : conv1d_tc2_kernel<KQ, SEP_ACT_LINEAR, true>;
+    else kern = act == SEP_ACT_SIGMOID ? conv1d_tc2_kernel<KQ, SEP_ACT_SIGMOID, false>
+                : act == SEP_ACT_RELU  ? conv1d_tc2_kernel<KQ, SEP_ACT_RELU, false>
+                                       : conv1d_tc2_kernel<KQ, SEP_ACT_LINEAR, false>;
+    const size_t smem_k = xs ? smem3 : smem2;
+    SEP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_k)));
     const int64_t tiles = (static_cast<int64_t>(batch) * rows_out + kCtM - 1) / kCtM;
     const int grid = static_cast<int>(std::min<int64_t>(tiles, sms));
-    profile_begin(stream, "conv1d_tc2_kernel<K=%d> (tcgen05 kind::tf32 x3, A in TMEM x2, M=128 N=%d, output tiles by "
-                  "cp.async.bulk; taps=%d c_in=%d filters=%d stride=%d)", K, NP, taps, c_in, filters, stride);
-    kern<<<grid, kCt2Threads, smem2, stream>>>(a);
+    profile_begin(stream, "conv1d_tc2_kernel<K=%d%s> (tcgen05 kind::tf32 x3, A in TMEM, M=128 N=%d, output tiles by "
+                  "cp.async.bulk; taps=%d c_in=%d filters=%d stride=%d)", K, xs ? ",XS" : "", NP, taps, c_in, filters, stride);
+    kern<<<grid, kCt2Threads, smem_k, stream>>>(a);
     profile_end(stream);
     SEP_LAUNCHED();
     return SEP_OK;

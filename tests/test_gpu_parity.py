@@ -742,6 +742,10 @@ def test_conv1d_weights_resident_kernel(sep, oracle, monkeypatch, batch, rows, c
     simt = sep.conv1d(x, w, bias, stride=stride, padding=padding, activation=act)
     monkeypatch.delenv("SEPCORE_CONV_SIMT")
     assert np.max(np.abs(simt - want)) < 2e-5 and np.max(np.abs(simt - got)) < 1e-5
+    monkeypatch.setenv("SEPCORE_CONV_XS", "0")       # x rows by per-thread loads instead of the bulk-copied tile span
+    noxs = sep.conv1d(x, w, bias, stride=stride, padding=padding, activation=act)
+    monkeypatch.delenv("SEPCORE_CONV_XS")
+    assert np.array_equal(noxs, got)
     monkeypatch.setenv("SEPCORE_CONV_TC1", "1")      # the two tcgen05 kernels against each other
     tc1 = sep.conv1d(x, w, bias, stride=stride, padding=padding, activation=act)
     monkeypatch.delenv("SEPCORE_CONV_TC1")
